@@ -1,0 +1,98 @@
+// Internal declarations shared by the kernels and the C-ABI host runtime.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace aur {
+
+// ---------------------------------------------------------------- candidate keys
+// A candidate is one uint64: high word = order-preserving image of the fp32 score, low
+// word = ~row so that, for equal scores, the LOWER row index compares GREATER.  Sorting
+// keys in descending order therefore yields (score desc, row asc).
+constexpr uint64_t kKeyEmpty = 0x007FFFFF00000000ull;  // score -inf, row -1
+__host__ __device__ __forceinline__ uint32_t f32_to_ord(float f) {
+#ifdef __CUDA_ARCH__
+  uint32_t u = __float_as_uint(f);
+#else
+  union { float f; uint32_t u; } c; c.f = f; uint32_t u = c.u;
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord_to_f32(uint32_t o) {
+  uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+__host__ __device__ __forceinline__ uint64_t make_key(float score, int32_t row) {
+  return (static_cast<uint64_t>(f32_to_ord(score)) << 32) | static_cast<uint32_t>(~row);
+}
+__host__ __device__ __forceinline__ int32_t key_row(uint64_t k) { return static_cast<int32_t>(~static_cast<uint32_t>(k)); }
+__host__ __device__ __forceinline__ float key_score(uint64_t k) { return ord_to_f32(static_cast<uint32_t>(k >> 32)); }
+
+// ---------------------------------------------------------------- tcgen05 similarity kernel
+constexpr int kTcTileN = 64;       // corpus rows per tile  (MMA N)
+constexpr int kTcKBlock = 64;      // bf16 per 128-byte swizzled smem row
+constexpr int kTcKbPerStage = 4;   // k-blocks per pipeline stage
+constexpr int kTcQRows = 128;      // queries per CTA (TMEM lanes)
+constexpr int kTcPendCap = 32;     // pending candidates per query between drains
+constexpr int kTcThreads = 192;    // producer warp, MMA warp, 4 epilogue warps
+constexpr int kTcMaxStages = 8;
+constexpr int kTcMaxDim = 768;     // A operand (queries) must fit 384 TMEM columns
+constexpr int kTcAccCol0 = 384;    // accumulator buffers at TMEM columns 384 / 448
+constexpr int kSlack = 8;          // extra candidates kept for the exact re-rank
+constexpr int kMaxK = 128;
+
+struct TcParams {
+  const __nv_bfloat16* q;   // [nq, dim] queries of this launch (<= 128 * n_qblocks)
+  const float* inv_norm;    // [n_rows]   1/|c_j|, 0 for zero rows, NaN for tombstones
+  uint64_t* cand;           // [128 * n_qblocks, n_lists, ksel] candidate keys (out)
+  float* dbg_scores;        // optional [grid, 128, 64]: first tile's scores of every CTA
+  int64_t n_rows;
+  int nq, dim, ksel, n_lists, n_qblocks, num_stages, n_tiles;
+};
+
+size_t tc_smem_bytes(int cta_group, int num_stages, int ksel);
+int tc_pick_stages(int cta_group, int ksel, size_t smem_limit);
+// Launches the fused similarity + top-k kernel.  tmap: CUtensorMap over the corpus with a
+// {64, 64 / cta_group} box and 128-byte swizzle.
+cudaError_t tc_launch(int cta_group, int grid, const void* tmap, const TcParams& p, size_t smem, cudaStream_t s);
+
+// ---------------------------------------------------------------- SIMT kernels
+struct FilterArgs {
+  const int32_t* row_user;  // [n_rows]
+  const int32_t* row_org;   // [n_rows]
+  const int32_t* q_user;    // [nq]   (nullptr = unfiltered)
+  const int32_t* q_org;     // [nq]   (nullptr = none)
+};
+
+cudaError_t launch_row_inv_norms(const void* rows, int dtype, int dim, int64_t n, float* inv_norm, cudaStream_t s);
+// Generic path: scores of a chunk of rows for all queries, then per-segment selection.
+constexpr int kSimtSeg = 2048;    // corpus rows per selection segment (one candidate list)
+cudaError_t launch_simt_scores(const void* q, const void* rows, int dtype, int dim, int nq, int64_t row0,
+                               int64_t nrows_chunk, int64_t n_rows, const float* inv_norm, FilterArgs f,
+                               float* scores /* [nq, nrows_chunk] */, cudaStream_t s);
+cudaError_t launch_simt_select(const float* scores, int nq, int64_t row0, int64_t nrows_chunk, int ksel,
+                               uint64_t* cand, int n_lists, int list0, cudaStream_t s);
+// [nq, n_lists, ksel] -> [nq, ceil(n_lists/group), ksel]; group*ksel <= 4096
+cudaError_t launch_reduce_lists(const uint64_t* in, int nq, int n_lists, int ksel, int group, uint64_t* out,
+                                cudaStream_t s);
+// Final stage: best ksel of n_lists*ksel (<= 4096) keys, exact fp64 cosine re-rank,
+// (score desc, id asc) order, top-k out.
+struct FinalizeArgs {
+  const uint64_t* cand; int n_lists; int ksel;
+  const void* q; const void* rows; int dtype; int dim; int nq; int k;
+  const int64_t* ids;
+  float* out_scores; int64_t* out_ids; double* out_scores64;
+};
+cudaError_t launch_finalize(const FinalizeArgs& a, cudaStream_t s);
+cudaError_t launch_merge_topk(const double* in_s, const int64_t* in_ids, int n_shards, int nq, int k,
+                              float* out_s, int64_t* out_ids, double* out_s64, cudaStream_t s);
+cudaError_t launch_cosine_pairs(const float* a, const float* b, int64_t n, int dim, int clamp, double* out,
+                                cudaStream_t s);
+cudaError_t launch_fill_f32(float* p, float v, int64_t n, cudaStream_t s);
+
+}  // namespace aur

@@ -1,0 +1,378 @@
+// CUDA-core kernels of the retrieval path: ingest-time inverse norms, the generic
+// (any dim / dtype / tenant-filter) similarity path, candidate-list reduction, the exact
+// fp64 re-rank that fixes the final (score desc, id asc) order, the cross-shard merge and
+// the pairwise cosine that mirrors SimilarityStrategy._cosine_similarity.
+#include <math.h>
+#include "internal.h"
+
+namespace aur {
+namespace {
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+__device__ __forceinline__ double warp_sum_lane0(double v) {
+  // shfl_down tree: lane 0 ends with a value whose association order is fixed, so the
+  // result for a row depends only on the row's content.
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return __shfl_sync(0xffffffffu, v, 0);
+}
+
+// --------------------------------------------------------------------------------------
+// Inverse L2 norm per appended row (one warp per row).  Weaviate normalises vectors at
+// import for the cosine metric; we keep the raw rows and this scale beside them.
+template <typename T>
+__global__ void row_inv_norm_kernel(const T* __restrict__ rows, int dim, int64_t n, float* __restrict__ inv_norm) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const T* p = rows + row * dim;
+  float ss = 0.f;
+  for (int i = lane; i < dim; i += 32) { const float v = to_f32(p[i]); ss = fmaf(v, v, ss); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane == 0) inv_norm[row] = ss > 0.f ? 1.0f / sqrtf(ss) : 0.f;
+}
+
+// --------------------------------------------------------------------------------------
+// Generic similarity: 64 queries x 64 rows per block, 4x4 per thread, fp32 FMA.
+constexpr int kSB = 64, kSK = 16;
+template <typename T>
+__global__ void __launch_bounds__(256)
+simt_scores_kernel(const T* __restrict__ q, const T* __restrict__ rows, int dim, int nq, int64_t row0,
+                   int64_t nrows_chunk, int64_t n_rows, const float* __restrict__ inv_norm, FilterArgs f,
+                   float* __restrict__ scores) {
+  __shared__ float Qs[kSK][kSB + 1];
+  __shared__ float Cs[kSK][kSB + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int q0 = blockIdx.y * kSB;
+  const int64_t c0 = static_cast<int64_t>(blockIdx.x) * kSB;  // within chunk
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < dim; k0 += kSK) {
+    for (int i = threadIdx.x; i < kSB * kSK; i += 256) {
+      const int rr = i / kSK, kk = i % kSK;
+      const int k = k0 + kk;
+      float qv = 0.f, cv = 0.f;
+      if (k < dim) {
+        if (q0 + rr < nq) qv = to_f32(q[static_cast<size_t>(q0 + rr) * dim + k]);
+        const int64_t row = row0 + c0 + rr;
+        if (c0 + rr < nrows_chunk && row < n_rows) cv = to_f32(rows[row * dim + k]);
+      }
+      Qs[kk][rr] = qv; Cs[kk][rr] = cv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kSK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = Qs[kk][ty * 4 + i]; b[i] = Cs[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int qi = q0 + ty * 4 + i;
+    if (qi >= nq) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t cj = c0 + tx * 4 + j;
+      if (cj >= nrows_chunk) continue;
+      const int64_t row = row0 + cj;
+      float s = -INFINITY;
+      if (row < n_rows) {
+        const float nv = inv_norm[row];
+        bool ok = (nv == nv);  // NaN = tombstone
+        if (ok && f.q_user != nullptr) {
+          // weaviate_client.py:244-249: user_id == u OR (org given AND org_id == o)
+          const int32_t qo = f.q_org ? f.q_org[qi] : -1;
+          ok = (f.row_user[row] == f.q_user[qi]) || (qo >= 0 && f.row_org[row] == qo);
+        }
+        if (ok) s = acc[i][j] * nv;
+      }
+      scores[static_cast<size_t>(qi) * nrows_chunk + cj] = s;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// Block-wide bitonic sort, descending, n a power of two, keys in shared memory.
+__device__ void bitonic_desc(uint64_t* s, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const uint64_t a = s[i], b = s[l];
+          const bool desc = (i & k) == 0;
+          if ((a < b) == desc) { s[i] = b; s[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// One block per (segment of kSimtSeg scores, query): keep the best ksel as keys.
+__global__ void __launch_bounds__(256)
+simt_select_kernel(const float* __restrict__ scores, int64_t row0, int64_t nrows_chunk, int ksel,
+                   uint64_t* __restrict__ cand, int n_lists, int list0) {
+  __shared__ uint64_t keys[kSimtSeg];
+  const int seg = blockIdx.x, qi = blockIdx.y;
+  const int64_t base = static_cast<int64_t>(seg) * kSimtSeg;
+  for (int i = threadIdx.x; i < kSimtSeg; i += blockDim.x) {
+    const int64_t cj = base + i;
+    uint64_t key = 0;
+    if (cj < nrows_chunk) {
+      const float s = scores[static_cast<size_t>(qi) * nrows_chunk + cj];
+      key = (s == -INFINITY || s != s) ? kKeyEmpty : make_key(s, static_cast<int32_t>(row0 + cj));
+    }
+    keys[i] = key;
+  }
+  __syncthreads();
+  bitonic_desc(keys, kSimtSeg);
+  uint64_t* out = cand + (static_cast<size_t>(qi) * n_lists + list0 + seg) * ksel;
+  for (int t = threadIdx.x; t < ksel; t += blockDim.x) out[t] = keys[t] == 0 ? kKeyEmpty : keys[t];
+}
+
+constexpr int kSortCap = 4096;
+
+// [nq, n_lists, ksel] -> [nq, n_groups, ksel]
+__global__ void __launch_bounds__(512)
+reduce_lists_kernel(const uint64_t* __restrict__ in, int n_lists, int ksel, int group, uint64_t* __restrict__ out,
+                    int n_groups) {
+  extern __shared__ uint64_t skeys[];
+  const int g = blockIdx.x, qi = blockIdx.y;
+  const int l0 = g * group, l1 = min(n_lists, l0 + group);
+  const int n = (l1 - l0) * ksel;
+  int P = 1; while (P < n) P <<= 1;
+  const uint64_t* src = in + (static_cast<size_t>(qi) * n_lists + l0) * ksel;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) skeys[i] = i < n ? src[i] : 0ull;
+  __syncthreads();
+  bitonic_desc(skeys, P);
+  uint64_t* dst = out + (static_cast<size_t>(qi) * n_groups + g) * ksel;
+  for (int t = threadIdx.x; t < ksel; t += blockDim.x) dst[t] = (t < P && skeys[t] != 0) ? skeys[t] : kKeyEmpty;
+}
+
+// --------------------------------------------------------------------------------------
+// Finalize: best ksel approximate candidates -> exact fp64 cosine -> (score desc, id asc).
+template <typename T>
+__global__ void __launch_bounds__(512)
+finalize_kernel(FinalizeArgs a) {
+  extern __shared__ uint64_t skeys[];
+  __shared__ double ex_score[kMaxK + kSlack];
+  __shared__ int64_t ex_id[kMaxK + kSlack];
+  __shared__ double s_qq;
+  const int qi = blockIdx.x;
+  const int n = a.n_lists * a.ksel;
+  int P = 1; while (P < n) P <<= 1;
+  const uint64_t* src = a.cand + static_cast<size_t>(qi) * n;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) skeys[i] = i < n ? src[i] : 0ull;
+  __syncthreads();
+  bitonic_desc(skeys, P);
+
+  const T* rows = static_cast<const T*>(a.rows);
+  const T* qv = static_cast<const T*>(a.q) + static_cast<size_t>(qi) * a.dim;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  if (warp == 0) {
+    double qq = 0.0;
+    for (int i = lane; i < a.dim; i += 32) { const double v = static_cast<double>(to_f32(qv[i])); qq = fma(v, v, qq); }
+    qq = warp_sum_lane0(qq);
+    if (lane == 0) s_qq = qq;
+  }
+  __syncthreads();
+  const int ncand = min(a.ksel, P);
+  for (int c = warp; c < ncand; c += nwarps) {
+    const uint64_t key = skeys[c];
+    const int32_t row = (key == 0) ? -1 : key_row(key);
+    double sc = -INFINITY; int64_t id = -1;
+    if (row >= 0) {  // warp-uniform
+      const T* rv = rows + static_cast<size_t>(row) * a.dim;
+      double dot = 0.0, cc = 0.0;
+      for (int i = lane; i < a.dim; i += 32) {
+        const double x = static_cast<double>(to_f32(qv[i])), y = static_cast<double>(to_f32(rv[i]));
+        dot = fma(x, y, dot); cc = fma(y, y, cc);
+      }
+      dot = warp_sum_lane0(dot); cc = warp_sum_lane0(cc);
+      const double den = sqrt(s_qq) * sqrt(cc);
+      sc = den > 0.0 ? dot / den : 0.0;  // zero norm -> 0.0 (similarity.py:94-95)
+      id = a.ids[row];
+    }
+    if (lane == 0) { ex_score[c] = sc; ex_id[c] = id; }
+  }
+  __syncthreads();
+  // rank by counting: ids are unique, so (score desc, id asc) is a total order
+  for (int t = threadIdx.x; t < ncand; t += blockDim.x) {
+    const double s = ex_score[t]; const int64_t id = ex_id[t];
+    if (id < 0) continue;
+    int rank = 0;
+    for (int u = 0; u < ncand; ++u) {
+      const double su = ex_score[u]; const int64_t iu = ex_id[u];
+      if (iu >= 0 && (su > s || (su == s && iu < id))) ++rank;
+    }
+    if (rank < a.k) {
+      const size_t o = static_cast<size_t>(qi) * a.k + rank;
+      a.out_scores[o] = static_cast<float>(s); a.out_ids[o] = id;
+      if (a.out_scores64) a.out_scores64[o] = s;
+    }
+  }
+  __shared__ int s_nvalid;
+  if (threadIdx.x == 0) { int nv = 0; for (int u = 0; u < ncand; ++u) nv += ex_id[u] >= 0; s_nvalid = nv; }
+  __syncthreads();
+  for (int t = s_nvalid + threadIdx.x; t < a.k; t += blockDim.x) {
+    const size_t o = static_cast<size_t>(qi) * a.k + t;
+    a.out_scores[o] = -INFINITY; a.out_ids[o] = -1;
+    if (a.out_scores64) a.out_scores64[o] = -INFINITY;
+  }
+}
+
+// Cross-shard merge of exact (fp64 score, id) lists: [n_shards, nq, k] -> [nq, k].
+__global__ void __launch_bounds__(256)
+merge_topk_kernel(const double* __restrict__ in_s, const int64_t* __restrict__ in_ids, int n_shards, int nq, int k,
+                  float* out_s, int64_t* out_ids, double* out_s64) {
+  extern __shared__ uint8_t sm[];
+  double* sc = reinterpret_cast<double*>(sm);
+  int64_t* id = reinterpret_cast<int64_t*>(sc + n_shards * k);
+  __shared__ int s_nvalid;
+  const int qi = blockIdx.x, n = n_shards * k;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int sh = i / k, t = i % k;
+    const size_t o = (static_cast<size_t>(sh) * nq + qi) * k + t;
+    sc[i] = in_s[o]; id[i] = in_ids[o];
+  }
+  if (threadIdx.x == 0) s_nvalid = 0;
+  __syncthreads();
+  int local_valid = 0;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    const double s = sc[t]; const int64_t me = id[t];
+    if (me < 0) continue;
+    ++local_valid;
+    int rank = 0;
+    for (int u = 0; u < n; ++u) {
+      const double su = sc[u]; const int64_t iu = id[u];
+      if (iu >= 0 && (su > s || (su == s && iu < me))) ++rank;
+    }
+    if (rank < k) {
+      const size_t o = static_cast<size_t>(qi) * k + rank;
+      out_s[o] = static_cast<float>(s); out_ids[o] = me;
+      if (out_s64) out_s64[o] = s;
+    }
+  }
+  atomicAdd(&s_nvalid, local_valid);
+  __syncthreads();
+  for (int t = s_nvalid + threadIdx.x; t < k; t += blockDim.x) {
+    const size_t o = static_cast<size_t>(qi) * k + t;
+    out_s[o] = -INFINITY; out_ids[o] = -1;
+    if (out_s64) out_s64[o] = -INFINITY;
+  }
+}
+
+// Pairwise cosine, fp64 accumulate, optional [0,1] clamp (similarity.py:84-98).
+__global__ void cosine_pairs_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, int dim,
+                                    int clamp, double* __restrict__ out) {
+  const int64_t pair = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (pair >= n) return;
+  const float* x = a + pair * dim; const float* y = b + pair * dim;
+  double dot = 0.0, xx = 0.0, yy = 0.0;
+  for (int i = lane; i < dim; i += 32) {
+    const double u = x[i], v = y[i];
+    dot = fma(u, v, dot); xx = fma(u, u, xx); yy = fma(v, v, yy);
+  }
+  dot = warp_sum_lane0(dot); xx = warp_sum_lane0(xx); yy = warp_sum_lane0(yy);
+  if (lane == 0) {
+    const double den = sqrt(xx) * sqrt(yy);
+    double c = (dim > 0 && den > 0.0) ? dot / den : 0.0;
+    if (clamp) c = fmax(0.0, fmin(1.0, c));
+    out[pair] = c;
+  }
+}
+
+__global__ void fill_f32_kernel(float* p, float v, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace
+
+cudaError_t launch_row_inv_norms(const void* rows, int dtype, int dim, int64_t n, float* inv_norm, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  const int threads = 256;
+  const int64_t blocks = (n * 32 + threads - 1) / threads;
+  if (dtype == 0)
+    row_inv_norm_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), threads, 0, s>>>(
+        static_cast<const __nv_bfloat16*>(rows), dim, n, inv_norm);
+  else
+    row_inv_norm_kernel<float><<<static_cast<unsigned>(blocks), threads, 0, s>>>(static_cast<const float*>(rows), dim, n,
+                                                                               inv_norm);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_simt_scores(const void* q, const void* rows, int dtype, int dim, int nq, int64_t row0,
+                               int64_t nrows_chunk, int64_t n_rows, const float* inv_norm, FilterArgs f, float* scores,
+                               cudaStream_t s) {
+  dim3 grid(static_cast<unsigned>((nrows_chunk + kSB - 1) / kSB), static_cast<unsigned>((nq + kSB - 1) / kSB));
+  if (dtype == 0)
+    simt_scores_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(q),
+                                                          static_cast<const __nv_bfloat16*>(rows), dim, nq, row0,
+                                                          nrows_chunk, n_rows, inv_norm, f, scores);
+  else
+    simt_scores_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(q), static_cast<const float*>(rows), dim, nq,
+                                                  row0, nrows_chunk, n_rows, inv_norm, f, scores);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_simt_select(const float* scores, int nq, int64_t row0, int64_t nrows_chunk, int ksel, uint64_t* cand,
+                               int n_lists, int list0, cudaStream_t s) {
+  dim3 grid(static_cast<unsigned>((nrows_chunk + kSimtSeg - 1) / kSimtSeg), static_cast<unsigned>(nq));
+  simt_select_kernel<<<grid, 256, 0, s>>>(scores, row0, nrows_chunk, ksel, cand, n_lists, list0);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_lists(const uint64_t* in, int nq, int n_lists, int ksel, int group, uint64_t* out,
+                                cudaStream_t s) {
+  const int n_groups = (n_lists + group - 1) / group;
+  int P = 1; while (P < group * ksel) P <<= 1;
+  dim3 grid(static_cast<unsigned>(n_groups), static_cast<unsigned>(nq));
+  reduce_lists_kernel<<<grid, 512, static_cast<size_t>(P) * 8, s>>>(in, n_lists, ksel, group, out, n_groups);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_finalize(const FinalizeArgs& a, cudaStream_t s) {
+  int P = 1; while (P < a.n_lists * a.ksel) P <<= 1;
+  if (P > kSortCap) return cudaErrorInvalidValue;
+  const size_t smem = static_cast<size_t>(P) * 8;
+  if (a.dtype == 0) finalize_kernel<__nv_bfloat16><<<a.nq, 512, smem, s>>>(a);
+  else finalize_kernel<float><<<a.nq, 512, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_merge_topk(const double* in_s, const int64_t* in_ids, int n_shards, int nq, int k, float* out_s,
+                              int64_t* out_ids, double* out_s64, cudaStream_t s) {
+  const size_t smem = static_cast<size_t>(n_shards) * k * 16;
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  merge_topk_kernel<<<nq, 256, smem, s>>>(in_s, in_ids, n_shards, nq, k, out_s, out_ids, out_s64);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cosine_pairs(const float* a, const float* b, int64_t n, int dim, int clamp, double* out,
+                                cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  const int threads = 256;
+  const int64_t blocks = (n * 32 + threads - 1) / threads;
+  cosine_pairs_kernel<<<static_cast<unsigned>(blocks), threads, 0, s>>>(a, b, n, dim, clamp, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fill_f32(float* p, float v, int64_t n, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  fill_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(p, v, n);
+  return cudaGetLastError();
+}
+
+}  // namespace aur

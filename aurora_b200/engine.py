@@ -1,0 +1,185 @@
+"""Python handle over one corpus shard in HBM (the C ABI of include/aurora_b200.h).
+
+numpy in / numpy out for the host entry points; ``*_dev`` methods take raw device
+pointers (``tensor.data_ptr()``) so torch is only plumbing for memory and streams.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _native as N
+
+
+def to_bf16_bits(x: np.ndarray) -> np.ndarray:
+    """fp32 -> bf16 bit patterns (uint16), round-to-nearest-even.  Host-side format
+    conversion of inputs only; no scoring happens on the CPU."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    r = u + np.uint32(0x7FFF) + ((u >> np.uint32(16)) & np.uint32(1))
+    return (r >> np.uint32(16)).astype(np.uint16)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Index:
+    """One row-shard of the corpus, resident on one GPU."""
+
+    def __init__(self, dim: int, capacity: int, dtype: str = "bf16", device: int = 0):
+        self._lib = N.load()
+        self.dim, self.capacity, self.device = int(dim), int(capacity), int(device)
+        self.dtype = {"bf16": N.AUR_BF16, "f32": N.AUR_F32}[dtype]
+        self._h = C.c_void_p()
+        cfg = N.AurConfig(device=self.device, dim=self.dim, dtype=self.dtype, reserved=0, capacity=self.capacity)
+        N.check(self._lib.aur_open(C.byref(cfg), C.byref(self._h)))
+
+    # -------------------------------------------------------------- lifecycle
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.aur_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -------------------------------------------------------------- helpers
+    def _rows_buffer(self, x: np.ndarray) -> np.ndarray:
+        x = np.asarray(x)
+        if x.ndim != 2 or x.shape[1] != self.dim:
+            raise ValueError(f"expected [n, {self.dim}] rows, got {x.shape}")
+        if self.dtype == N.AUR_BF16:
+            if x.dtype == np.uint16:
+                return np.ascontiguousarray(x)
+            return to_bf16_bits(x)
+        return np.ascontiguousarray(x, dtype=np.float32)
+
+    # -------------------------------------------------------------- ingest
+    def add(self, rows: np.ndarray, ids: np.ndarray, user_codes: Optional[np.ndarray] = None,
+            org_codes: Optional[np.ndarray] = None) -> None:
+        buf = self._rows_buffer(rows)
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        if ids.shape != (buf.shape[0],):
+            raise ValueError("ids must be [n]")
+        u = None if user_codes is None else np.ascontiguousarray(user_codes, dtype=np.int32)
+        o = None if org_codes is None else np.ascontiguousarray(org_codes, dtype=np.int32)
+        N.check(self._lib.aur_add(self._h, _ptr(buf), _ptr(ids), _ptr(u), _ptr(o), buf.shape[0]))
+
+    def add_dev(self, rows_ptr: int, n: int, ids: np.ndarray, user_codes=None, org_codes=None, stream: int = 0) -> None:
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        u = None if user_codes is None else np.ascontiguousarray(user_codes, dtype=np.int32)
+        o = None if org_codes is None else np.ascontiguousarray(org_codes, dtype=np.int32)
+        N.check(self._lib.aur_add_dev(self._h, C.c_void_p(rows_ptr), _ptr(ids), _ptr(u), _ptr(o), int(n),
+                                      C.c_void_p(stream)))
+
+    def remove(self, ids) -> int:
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        removed = C.c_int64(0)
+        N.check(self._lib.aur_remove(self._h, _ptr(ids), ids.shape[0], C.byref(removed)))
+        return int(removed.value)
+
+    # -------------------------------------------------------------- search
+    def search(self, queries: np.ndarray, k: int, q_user: Optional[np.ndarray] = None,
+               q_org: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
+        """Host buffers in, host buffers out: (ids [nq,k] int64, scores [nq,k] float32)."""
+        q = self._rows_buffer(queries)
+        nq = q.shape[0]
+        scores = np.empty((nq, k), dtype=np.float32)
+        ids = np.empty((nq, k), dtype=np.int64)
+        u = None if q_user is None else np.ascontiguousarray(q_user, dtype=np.int32)
+        o = None if q_org is None else np.ascontiguousarray(q_org, dtype=np.int32)
+        N.check(self._lib.aur_search(self._h, _ptr(q), nq, int(k), _ptr(u), _ptr(o), _ptr(scores), _ptr(ids)))
+        return ids, scores
+
+    def search_dev(self, q_ptr: int, nq: int, k: int, scores_ptr: int, ids_ptr: int, scores64_ptr: int = 0,
+                   q_user_ptr: int = 0, q_org_ptr: int = 0, stream: int = 0) -> None:
+        """Everything in HBM; asynchronous on ``stream`` (0 = the index's own stream)."""
+        N.check(self._lib.aur_search_dev(self._h, C.c_void_p(q_ptr), int(nq), int(k), C.c_void_p(q_user_ptr),
+                                         C.c_void_p(q_org_ptr), C.c_void_p(scores_ptr), C.c_void_p(ids_ptr),
+                                         C.c_void_p(scores64_ptr), C.c_void_p(stream)))
+
+    def debug_tc_scores(self, q_ptr: int, nq: int, cta_group: int, out_ptr: int, stream: int = 0) -> int:
+        n = C.c_int32(0)
+        N.check(self._lib.aur_debug_tc_scores(self._h, C.c_void_p(q_ptr), int(nq), int(cta_group),
+                                              C.c_void_p(out_ptr), C.byref(n), C.c_void_p(stream)))
+        return int(n.value)
+
+    # -------------------------------------------------------------- misc
+    def set_kernel(self, kernel: int) -> None:
+        N.check(self._lib.aur_set_option(self._h, b"kernel", int(kernel)))
+
+    def sync(self) -> None:
+        N.check(self._lib.aur_sync(self._h))
+
+    def stats(self) -> dict:
+        st = N.AurStats()
+        N.check(self._lib.aur_get_stats(self._h, C.byref(st)))
+        return {f: getattr(st, f) for f, _ in N.AurStats._fields_}
+
+
+def merge_topk_dev(device: int, in_scores64_ptr: int, in_ids_ptr: int, n_shards: int, nq: int, k: int,
+                   out_scores_ptr: int, out_ids_ptr: int, out_scores64_ptr: int = 0, stream: int = 0) -> None:
+    lib = N.load()
+    N.check(lib.aur_merge_topk_dev(int(device), C.c_void_p(in_scores64_ptr), C.c_void_p(in_ids_ptr), int(n_shards),
+                                   int(nq), int(k), C.c_void_p(out_scores_ptr), C.c_void_p(out_ids_ptr),
+                                   C.c_void_p(out_scores64_ptr), C.c_void_p(stream)))
+
+
+def cosine_pairs(a: np.ndarray, b: np.ndarray, clamp: bool = False, device: int = 0) -> np.ndarray:
+    """Row-wise cosine on the GPU (fp64 accumulate).  Mirrors
+    SimilarityStrategy._cosine_similarity (similarity.py:84-98) for batches."""
+    lib = N.load()
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    if a.shape != b.shape or a.ndim != 2:
+        raise ValueError("a and b must both be [n, dim]")
+    out = np.empty(a.shape[0], dtype=np.float64)
+    N.check(lib.aur_cosine_pairs(int(device), _ptr(a), _ptr(b), a.shape[0], a.shape[1], int(bool(clamp)), _ptr(out)))
+    return out
+
+
+class DeviceBuffer:
+    """Raw HBM buffer owned through the C ABI (for callers without torch)."""
+
+    def __init__(self, nbytes: int, device: int = 0):
+        self._lib = N.load()
+        self.device, self.nbytes = int(device), int(nbytes)
+        p = C.c_void_p()
+        N.check(self._lib.aur_dev_malloc(self.device, self.nbytes, C.byref(p)))
+        self.ptr = int(p.value)
+
+    def upload(self, a: np.ndarray) -> "DeviceBuffer":
+        a = np.ascontiguousarray(a)
+        if a.nbytes > self.nbytes:
+            raise ValueError("buffer too small")
+        N.check(self._lib.aur_memcpy_h2d(self.device, C.c_void_p(self.ptr), _ptr(a), a.nbytes))
+        return self
+
+    def download(self, a: np.ndarray) -> np.ndarray:
+        if not a.flags["C_CONTIGUOUS"] or a.nbytes > self.nbytes:
+            raise ValueError("need a contiguous array no larger than the buffer")
+        N.check(self._lib.aur_memcpy_d2h(self.device, _ptr(a), C.c_void_p(self.ptr), a.nbytes))
+        return a
+
+    def free(self) -> None:
+        if self.ptr:
+            self._lib.aur_dev_free(self.device, C.c_void_p(self.ptr))
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -1,0 +1,154 @@
+/*
+ * aurora_b200.h -- C ABI of the B200-native retrieval engine behind Aurora's
+ * knowledge-base RAG path.
+ *
+ * The reference (Arvo-AI/aurora) has no FFI for this path: its boundary is the Python
+ * module server/routes/knowledge_base/weaviate_client.py, which forwards every call
+ * over gRPC to a Weaviate 1.27.6 server (vector index) and, through it, to the
+ * t2v-transformers container (text -> vector).  This header is what a ctypes binding in
+ * that module binds instead; each entry point cites the reference
+ * interface it replaces.  Plain pointers and sizes only; no torch / CUDA types.
+ *
+ * Conventions
+ *   - every function returns AUR_OK (0) or a negative aur_status; on failure no output
+ *     buffer has been written and aur_last_error() (thread-local) describes why;
+ *   - "host" entry points take host pointers and include the H2D / D2H copies;
+ *     "_dev" entry points take device pointers on the index's device and a cudaStream_t
+ *     passed as void* (NULL = the index's own stream) and do not synchronise;
+ *   - vectors are row-major [n, dim]; dtype is fixed per index (AUR_BF16: raw uint16
+ *     bfloat16 bits; AUR_F32: IEEE float);
+ *   - ids are caller-chosen int64 (>= 0), unique per index; adding an existing id
+ *     replaces the old row (reference: deterministic uuid5 upsert,
+ *     weaviate_client.py:172);
+ *   - scores are cosine similarity (= 1 - Weaviate cosine distance, cf.
+ *     server/routes/incident_feedback/weaviate_client.py:296-297), NOT clamped;
+ *     results are ordered (score desc, id asc); missing results are padded with
+ *     id -1 / score -INFINITY;
+ *   - all entry points are thread-safe (one internal mutex per index) and never touch
+ *     the Python GIL.
+ */
+#ifndef AURORA_B200_H_
+#define AURORA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AUR_ABI_VERSION 1
+
+typedef enum aur_status {
+  AUR_OK = 0,
+  AUR_ERR_INVALID = -1,     /* bad argument                                   */
+  AUR_ERR_CUDA = -2,        /* CUDA runtime / driver error                    */
+  AUR_ERR_NOMEM = -3,       /* capacity exceeded or allocation failure        */
+  AUR_ERR_UNSUPPORTED = -4, /* shape / dtype not supported by the chosen path */
+  AUR_ERR_NO_DEVICE = -5    /* no CUDA device (the library has no CPU path)   */
+} aur_status;
+
+typedef enum aur_dtype { AUR_BF16 = 0, AUR_F32 = 1 } aur_dtype;
+
+/* Which similarity kernel serves a search (aur_set_option "kernel"). */
+typedef enum aur_kernel {
+  AUR_KERNEL_AUTO = 0,   /* tcgen05 path when the shape allows it, else SIMT      */
+  AUR_KERNEL_SIMT = 1,   /* generic CUDA-core path (any dim / dtype / filter)     */
+  AUR_KERNEL_TC1 = 2,    /* tcgen05, one CTA per MMA  (cta_group::1)              */
+  AUR_KERNEL_TC2 = 3     /* tcgen05, CTA pairs        (cta_group::2)              */
+} aur_kernel;
+
+typedef struct aur_index aur_index; /* opaque: one corpus shard resident on one GPU */
+
+typedef struct aur_config {
+  int32_t device;     /* CUDA ordinal                                               */
+  int32_t dim;        /* vector dimension                                           */
+  int32_t dtype;      /* aur_dtype                                                  */
+  int32_t reserved;
+  int64_t capacity;   /* rows of HBM to reserve for this shard (grow = reopen)      */
+} aur_config;
+
+typedef struct aur_stats {
+  int64_t rows;          /* rows ever appended (including tombstones)               */
+  int64_t live;          /* rows visible to search                                  */
+  int64_t capacity;
+  int32_t dim, dtype;
+  int32_t last_kernel;   /* aur_kernel actually used by the last search             */
+  int32_t last_launches; /* kernels launched by the last search                     */
+  float   last_kernel_ms;/* device time of the dominant kernel of the last search   */
+  float   last_total_ms; /* device time of the whole last search                    */
+} aur_stats;
+
+int aur_abi_version(void);
+const char* aur_last_error(void);
+int aur_device_count(void);
+
+/* Lifecycle.  Replaces weaviate.connect_to_local / _ensure_collection
+ * (weaviate_client.py:35-133): the "collection" is this shard. */
+int aur_open(const aur_config* cfg, aur_index** out);
+int aur_close(aur_index* ix);
+int aur_get_stats(aur_index* ix, aur_stats* out);
+int aur_set_option(aur_index* ix, const char* key, int64_t value);
+int aur_sync(aur_index* ix);
+
+/* Ingest.  Replaces collection.batch.dynamic()/add_object (weaviate_client.py:167-186)
+ * for already-embedded chunks: appends n rows, computes their inverse L2 norms on the
+ * device (Weaviate normalises at import for cosine).  user_codes / org_codes carry the
+ * tenant scope used by weaviate_client.py:244-249 as int32 codes (org -1 = none); both
+ * may be NULL (all rows get user 0, org -1). */
+int aur_add(aur_index* ix, const void* rows_host, const int64_t* ids,
+            const int32_t* user_codes, const int32_t* org_codes, int64_t n);
+int aur_add_dev(aur_index* ix, const void* rows_dev, const int64_t* ids_host,
+                const int32_t* user_codes_host, const int32_t* org_codes_host,
+                int64_t n, void* stream);
+
+/* Deletes.  Replaces collection.data.delete_many(where=...) (weaviate_client.py:309,
+ * :336, :387): the Python layer resolves the filter to ids; rows become tombstones.
+ * *removed receives how many ids were live. */
+int aur_remove(aur_index* ix, const int64_t* ids, int64_t n, int64_t* removed);
+
+/* Search.  Replaces the dense leg of collection.query.hybrid (weaviate_client.py:252-259)
+ * and collection.query.near_text (incident_feedback/weaviate_client.py:286-291), batched:
+ * nq queries at once, top-k each.  q_user / q_org: per-query tenant codes (NULL q_user =
+ * unfiltered; q_org may be NULL or hold -1 for "no org").
+ * scores_out [nq*k] float, ids_out [nq*k] int64. */
+int aur_search(aur_index* ix, const void* queries_host, int32_t nq, int32_t k,
+               const int32_t* q_user, const int32_t* q_org,
+               float* scores_out, int64_t* ids_out);
+/* Device variant: everything in HBM; scores64_dev (nullable) additionally receives the
+ * fp64 ranking keys needed for an exact cross-shard merge. */
+int aur_search_dev(aur_index* ix, const void* queries_dev, int32_t nq, int32_t k,
+                   const int32_t* q_user_dev, const int32_t* q_org_dev,
+                   float* scores_dev, int64_t* ids_dev, double* scores64_dev,
+                   void* stream);
+
+/* Cross-shard merge (row-sharded corpus over <= 8 GPUs): after an all-gather of each
+ * shard's (fp64 score, id) top-k, keep the best k per query on the device.
+ * in_scores64 / in_ids: [n_shards, nq, k]; out: [nq, k]. */
+int aur_merge_topk_dev(int32_t device, const double* in_scores64, const int64_t* in_ids,
+                       int32_t n_shards, int32_t nq, int32_t k,
+                       float* out_scores, int64_t* out_ids, double* out_scores64,
+                       void* stream);
+
+/* Pairwise cosine of row i of a with row i of b (host buffers, fp32 in, fp64 out).
+ * Replaces SimilarityStrategy._cosine_similarity
+ * (server/services/correlation/strategies/similarity.py:84-98); clamp != 0 applies its
+ * [0,1] clamp (:98). */
+int aur_cosine_pairs(int32_t device, const float* a_host, const float* b_host,
+                     int64_t n, int32_t dim, int32_t clamp, double* out_host);
+
+/* Raw device buffers for callers without a CUDA runtime of their own (ctypes tests, the
+ * benchmark's host-side staging).  Synchronous. */
+int aur_dev_malloc(int32_t device, uint64_t bytes, void** out);
+int aur_dev_free(int32_t device, void* p);
+int aur_memcpy_h2d(int32_t device, void* dst_dev, const void* src_host, uint64_t bytes);
+int aur_memcpy_d2h(int32_t device, void* dst_host, const void* src_dev, uint64_t bytes);
+
+/* Bring-up / test hooks (not part of the drop-in surface). */
+int aur_debug_tc_scores(aur_index* ix, const void* queries_dev, int32_t nq,
+                        int32_t cta_group, float* out_dev /* [n_ctas,128,64] */,
+                        int32_t* n_ctas_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AURORA_B200_H_ */
