@@ -1,0 +1,329 @@
+"""Drop-in for ``server/routes/knowledge_base/weaviate_client.py`` backed by the B200 engine.
+
+Same public names, keyword arguments, return shapes and error conventions as the
+reference module (file:line cited on every function), so its callers keep working
+unchanged:
+
+* ``routes/knowledge_base/routes.py:455-485``            (REST ``/search``)
+* ``chat/backend/agent/tools/knowledge_base_search_tool.py:61-70`` (LangGraph tool)
+* ``routes/knowledge_base/tasks.py:75-83``               (Celery ingest worker)
+* ``chat/backend/agent/tools/discovery_finding_tool.py:68-89``
+* ``chat/background/rca_prompt_builder.py:266-328``      (via ``_get_weaviate_client()``)
+
+What changes underneath: the Weaviate server (vector index) and the t2v-transformers
+container (text -> vector) are replaced by an in-HBM corpus shard searched with the
+fused similarity + top-k CUDA kernels (``aurora_b200.engine.Index``) and an encoder
+object.  Documented deviations: ``score`` is the cosine of the dense leg
+(the reference's hybrid call returns a ranked-fusion score; BM25 is a "next" row), and the
+embedded text is ``heading_context + "\\n" + content`` (the reference vectorises all TEXT
+properties, weaviate_client.py:113-126).
+
+There is no CPU fallback: without the CUDA library / a GPU the first call raises inside
+and the reference's own conventions apply (search -> ``[]``, insert re-raises, ...).
+"""
+
+from __future__ import annotations
+
+import logging
+import os
+import threading
+import uuid
+from datetime import datetime, timezone
+from types import SimpleNamespace
+from typing import Any, Callable, Dict, List, Optional
+
+import numpy as np
+
+from .filters import Filter, HybridFusion  # noqa: F401  (re-exported for call sites)
+
+logger = logging.getLogger(__name__)
+
+COLLECTION_NAME = "KnowledgeBaseChunk"  # weaviate_client.py:23
+_MAX_FETCH = 128                        # engine's largest k
+
+
+def _sanitize(value: Any) -> str:
+    """utils.log_sanitizer.sanitize stand-in: strip control characters from logged values."""
+    return "".join(ch if ch.isprintable() else "?" for ch in str(value))
+
+
+def generate_uuid5(identifier: str) -> str:
+    """weaviate.util.generate_uuid5 with the default (empty) namespace argument:
+    uuid5(NAMESPACE_DNS, str(identifier)).  Used for idempotent upserts (weaviate_client.py:172)."""
+    return str(uuid.uuid5(uuid.NAMESPACE_DNS, str(identifier)))
+
+
+class KnowledgeBase:
+    """Chunk store: vectors in the GPU index, properties in a host-side table.
+
+    ``encoder`` must provide ``dim`` and ``encode(list[str]) -> np.ndarray [n, dim]``
+    (float32 or bf16 bits).  ``index_factory(dim, capacity)`` builds the vector shard;
+    the default is the CUDA engine.
+    """
+
+    def __init__(self, encoder, capacity: int = 1 << 20, device: int = 0,
+                 index_factory: Optional[Callable[[int, int], Any]] = None):
+        if encoder is None:
+            raise RuntimeError("aurora_b200.retriever needs an encoder (text -> vector); none configured")
+        self.encoder = encoder
+        self.dim = int(encoder.dim)
+        if index_factory is None:
+            from .engine import Index  # raises loudly if the CUDA library is missing
+
+            def index_factory(dim, cap):
+                return Index(dim, cap, dtype="bf16", device=device)
+        self.index = index_factory(self.dim, int(capacity))
+        self._lock = threading.RLock()  # the reference's module globals are unlocked (weaviate_client.py:31-32)
+        self._props: Dict[int, Dict[str, Any]] = {}   # id -> properties
+        self._key2id: Dict[str, int] = {}             # uuid5 -> id
+        self._next_id = 0
+        self._user_code: Dict[str, int] = {}
+        self._org_code: Dict[str, int] = {}
+
+    # ------------------------------------------------------------------ tenant codes
+    def _code(self, table: Dict[str, int], key: Optional[str], create: bool) -> int:
+        if not key:
+            return -1
+        if key not in table:
+            if not create:
+                return -2  # matches no row
+            table[key] = len(table)
+        return table[key]
+
+    # ------------------------------------------------------------------ ingest
+    def insert(self, user_id: str, document_id: str, source_filename: str, chunks: List[Dict[str, Any]],
+               org_id: Optional[str] = None) -> int:
+        now = datetime.now(timezone.utc).isoformat()          # weaviate_client.py:165
+        texts, metas = [], []
+        for chunk in chunks:
+            try:
+                chunk_index = chunk.get("chunk_index", 0)
+                props = {
+                    "user_id": user_id, "document_id": document_id, "chunk_index": chunk_index,
+                    "content": chunk.get("content", ""), "heading_context": chunk.get("heading_context", ""),
+                    "source_filename": source_filename, "created_at": now,
+                }
+                if org_id:
+                    props["org_id"] = org_id               # weaviate_client.py:183-184
+                key = generate_uuid5(f"{user_id}:{document_id}:{chunk_index}")
+                heading = props["heading_context"]
+                texts.append((heading + "\n" if heading else "") + props["content"])
+                metas.append((key, props))
+            except Exception as e:  # per-object failure: counted out, not fatal (weaviate_client.py:189-190)
+                logger.error(f"[KB B200] Error adding chunk: {e}")
+        if not metas:
+            return 0
+        vecs = self.encoder.encode(texts)
+        with self._lock:
+            ids = np.empty(len(metas), dtype=np.int64)
+            for i, (key, _) in enumerate(metas):
+                if key not in self._key2id:
+                    self._key2id[key] = self._next_id
+                    self._next_id += 1
+                ids[i] = self._key2id[key]
+            ucode = np.full(len(metas), self._code(self._user_code, user_id, True), dtype=np.int32)
+            ocode = np.full(len(metas), self._code(self._org_code, org_id, True), dtype=np.int32)
+            self.index.add(vecs, ids, ucode, ocode)
+            for i, (_, props) in enumerate(metas):
+                self._props[int(ids[i])] = props
+        return len(metas)
+
+    # ------------------------------------------------------------------ search
+    def query(self, query: str, limit: int, filters=None, user_id: Optional[str] = None,
+              org_id: Optional[str] = None) -> List[SimpleNamespace]:
+        """Dense top-``limit``.  Tenant scope (user OR org) runs inside the kernel; any extra
+        ``filters`` expression is applied to the metadata of an over-fetched result."""
+        if limit <= 0:
+            return []
+        qv = self.encoder.encode([query])
+        with self._lock:
+            q_user = q_org = None
+            if user_id is not None or org_id is not None:
+                q_user = np.array([self._code(self._user_code, user_id, False) if user_id else -2], dtype=np.int32)
+                q_org = np.array([self._code(self._org_code, org_id, False) if org_id else -1], dtype=np.int32)
+                if q_org[0] == -2:
+                    q_org[0] = -1
+            fetch = limit if filters is None else _MAX_FETCH
+            fetch = max(1, min(_MAX_FETCH, fetch))
+            ids, scores = self.index.search(qv, fetch, q_user, q_org)
+            out = []
+            for rid, sc in zip(ids[0], scores[0]):
+                if rid < 0:
+                    break
+                props = self._props.get(int(rid))
+                if props is None or (filters is not None and not filters.matches(props)):
+                    continue
+                out.append(SimpleNamespace(properties=dict(props), uuid=None,
+                                           metadata=SimpleNamespace(score=float(sc), distance=1.0 - float(sc))))
+                if len(out) == limit:
+                    break
+            return out
+
+    # ------------------------------------------------------------------ deletes / counts
+    def _matching_ids(self, pred) -> List[int]:
+        return [rid for rid, p in self._props.items() if pred(p)]
+
+    def delete_where(self, pred) -> int:
+        with self._lock:
+            ids = self._matching_ids(pred)
+            if ids:
+                self.index.remove(np.array(ids, dtype=np.int64))
+                for rid in ids:
+                    p = self._props.pop(rid)
+                    self._key2id.pop(generate_uuid5(f"{p['user_id']}:{p['document_id']}:{p['chunk_index']}"), None)
+            return len(ids)
+
+    def count_where(self, pred) -> int:
+        with self._lock:
+            return len(self._matching_ids(pred))
+
+
+# ---------------------------------------------------------------------- façade for _get_weaviate_client()
+class _QueryFacade:
+    def __init__(self, kb: KnowledgeBase):
+        self._kb = kb
+
+    def hybrid(self, query: str, limit: int = 10, alpha: float = 0.5, fusion_type=None, filters=None,
+               return_metadata=None, **_):
+        return SimpleNamespace(objects=self._kb.query(query, limit, filters=filters))
+
+    def near_text(self, query: str, limit: int = 10, filters=None, return_metadata=None, **_):
+        return SimpleNamespace(objects=self._kb.query(query, limit, filters=filters))
+
+
+class _CollectionFacade:
+    """The slice of a weaviate Collection that rca_prompt_builder.py:291-317 touches."""
+
+    def __init__(self, kb: KnowledgeBase):
+        self.name = COLLECTION_NAME
+        self.query = _QueryFacade(kb)
+
+
+class _ClientFacade:
+    def is_ready(self) -> bool:
+        return True
+
+    def close(self) -> None:
+        pass
+
+
+# ---------------------------------------------------------------------- module state + configuration
+_kb: Optional[KnowledgeBase] = None
+_kb_factory: Optional[Callable[[], KnowledgeBase]] = None
+_state_lock = threading.Lock()
+
+
+def configure(encoder=None, capacity: Optional[int] = None, device: Optional[int] = None, index_factory=None,
+              factory: Optional[Callable[[], KnowledgeBase]] = None) -> None:
+    """Install the backend.  Environment: AURORA_B200_CAPACITY, AURORA_B200_DEVICE."""
+    global _kb, _kb_factory
+    with _state_lock:
+        _kb = None
+        if factory is not None:
+            _kb_factory = factory
+            return
+        cap = capacity if capacity is not None else int(os.getenv("AURORA_B200_CAPACITY", str(1 << 20)))
+        dev = device if device is not None else int(os.getenv("AURORA_B200_DEVICE", "0"))
+        _kb_factory = lambda: KnowledgeBase(encoder, capacity=cap, device=dev, index_factory=index_factory)  # noqa: E731
+
+
+def _get_kb() -> KnowledgeBase:
+    global _kb
+    with _state_lock:
+        if _kb is None:
+            if _kb_factory is None:
+                raise RuntimeError("aurora_b200.retriever is not configured: call configure(encoder=...) first")
+            _kb = _kb_factory()
+        return _kb
+
+
+def _get_weaviate_client():
+    """weaviate_client.py:35-101.  Returns (client, collection) façades; raises when the
+    backend cannot be created (the reference raises on connection failure, :99-101)."""
+    kb = _get_kb()
+    return _ClientFacade(), _CollectionFacade(kb)
+
+
+# ---------------------------------------------------------------------- public API (reference signatures)
+def insert_chunks(user_id: str, document_id: str, source_filename: str, chunks: List[Dict[str, Any]],
+                  org_id: str = None) -> int:
+    """weaviate_client.py:136-212.  [] -> 0; returns inserted count; backend failure re-raises
+    so the Celery task retries (tasks.py:100-111)."""
+    if not chunks:
+        return 0
+    try:
+        n = _get_kb().insert(user_id, document_id, source_filename, chunks, org_id)
+        logger.info(f"[KB B200] Successfully inserted {n} chunks for doc {document_id}")
+        return n
+    except Exception as e:
+        logger.error(f"[KB B200] Error inserting chunks: {e}")
+        raise
+
+
+def search_knowledge_base(user_id: str, query: str, limit: int = 5, alpha: float = 0.5, min_score: float = 0.0,
+                          org_id: str = None) -> List[Dict[str, Any]]:
+    """weaviate_client.py:215-285.  Blank query -> []; any exception -> log + [];
+    scope = user_id == u OR org_id == o (:244-249); min_score applies only if > 0 (:266)."""
+    if not query.strip():
+        return []
+    try:
+        objs = _get_kb().query(query, limit, user_id=user_id, org_id=org_id)
+        results = []
+        for obj in objs:
+            score = obj.metadata.score if obj.metadata else 0.0
+            if min_score > 0.0 and score < min_score:
+                continue
+            p = obj.properties
+            results.append({
+                "content": p.get("content", ""),
+                "heading_context": p.get("heading_context", ""),
+                "source_filename": p.get("source_filename", ""),
+                "document_id": p.get("document_id", ""),
+                "chunk_index": p.get("chunk_index", 0),
+                "score": score,
+            })
+        logger.info(f"[KB B200] Search for '{_sanitize(query)[:50]}...' returned {len(results)} results")
+        return results
+    except Exception as e:
+        logger.error(f"[KB B200] Error searching: {e}")
+        return []
+
+
+def delete_document_chunks(user_id: str, document_id: str) -> int:
+    """weaviate_client.py:288-319.  Deleted count; -1 on error."""
+    try:
+        return _get_kb().delete_where(lambda p: p.get("user_id") == user_id and p.get("document_id") == document_id)
+    except Exception as e:
+        logger.error(f"[KB B200] Error deleting chunks for doc {_sanitize(document_id)}: {_sanitize(e)}")
+        return -1
+
+
+def delete_user_chunks(user_id: str) -> int:
+    """weaviate_client.py:322-344.  Deleted count; -1 on error."""
+    try:
+        return _get_kb().delete_where(lambda p: p.get("user_id") == user_id)
+    except Exception as e:
+        logger.error(f"[KB B200] Error deleting chunks for user {_sanitize(user_id)}: {_sanitize(e)}")
+        return -1
+
+
+def get_document_chunk_count(user_id: str, document_id: str) -> int:
+    """weaviate_client.py:347-371.  0 on error."""
+    try:
+        return _get_kb().count_where(lambda p: p.get("user_id") == user_id and p.get("document_id") == document_id)
+    except Exception as e:
+        logger.error(f"[KB B200] Error getting chunk count: {e}")
+        return 0
+
+
+def delete_discovery_chunks(org_id: str, before: str = None) -> int:
+    """weaviate_client.py:374-394: org_id == o AND document_id LIKE 'discovery:*'
+    [AND created_at < before].  0 on error."""
+    try:
+        f = Filter.by_property("org_id").equal(org_id) & Filter.by_property("document_id").like("discovery:*")
+        if before:
+            f = f & Filter.by_property("created_at").less_than(before)
+        return _get_kb().delete_where(f.matches)
+    except Exception as e:
+        logger.error(f"[KB B200] Error deleting discovery chunks: {e}")
+        return 0

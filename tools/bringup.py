@@ -3,7 +3,7 @@
 kernel (mbarrier protocol bug) costs seconds, not the box.
 
   python tools/bringup.py            # run every stage, print a PASS/FAIL table
-  python tools/bringup.py <stage>    # run one stage in-process
+  python tools/bringup.py --stage <name>   # run one stage in-process
 
 Only numpy + ctypes (no torch import): start-up is fast on a fresh box.
 """
@@ -205,9 +205,9 @@ STAGES = {
 
 
 def main():
-    if len(sys.argv) > 1 and sys.argv[1] in STAGES:
-        ok = STAGES[sys.argv[1]][0]()
-        print("STAGE", sys.argv[1], "PASS" if ok else "FAIL")
+    if len(sys.argv) > 2 and sys.argv[1] == "--stage":
+        ok = STAGES[sys.argv[2]][0]()
+        print("STAGE", sys.argv[2], "PASS" if ok else "FAIL")
         sys.exit(0 if ok else 1)
     wanted = sys.argv[1:] or list(STAGES)
     results = {}
@@ -215,7 +215,7 @@ def main():
         fn, tmo = STAGES[name]
         t0 = time.time()
         try:
-            p = subprocess.run([sys.executable, os.path.abspath(__file__), name], timeout=tmo, capture_output=True, text=True)
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--stage", name], timeout=tmo, capture_output=True, text=True)
             out = p.stdout + p.stderr
             results[name] = "PASS" if p.returncode == 0 else f"FAIL(rc={p.returncode})"
         except subprocess.TimeoutExpired as e:
