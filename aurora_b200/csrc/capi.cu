@@ -92,6 +92,9 @@ struct aur_index {
   int opt_kernel = AUR_KERNEL_AUTO;
   int last_kernel = 0, last_launches = 0;
   DevBuf<uint64_t> cand_a, cand_b;
+  DevBuf<uint64_t> pub;          // tcgen05 kernel's cross-CTA threshold exchange
+  DevBuf<uint32_t> cand_count;   // compacted candidates per query (self-resetting)
+  uint32_t epoch = 0;
   DevBuf<float> score_chunk;
   DevBuf<uint8_t> stage_q;       // host-entry staging: queries
   DevBuf<int32_t> stage_quser, stage_qorg;
@@ -122,7 +125,7 @@ int build_tmaps(aur_index* ix) {
 }
 
 bool tc_shape_ok(const aur_index* ix, int k, bool filtered) {
-  return ix->tmap_ok && !filtered && k + kSlack <= kMaxK + kSlack;
+  return ix->tmap_ok && !filtered && k <= kMaxK;
 }
 
 // Runs one block of <= 256 queries through the tcgen05 kernel.  Leaves candidate keys in
@@ -138,11 +141,24 @@ int run_tc_block(aur_index* ix, int cta_group, const void* q_dev, int nqb, int k
   const size_t smem = tc_smem_bytes(cta_group, stages, ksel);
   const size_t ncand = static_cast<size_t>(n_qblocks) * kTcQRows * n_lists * ksel;
   CU_TRY(ix->cand_a.reserve(ncand));
+  const size_t npub = static_cast<size_t>(n_qblocks) * n_lists * kTcQRows;
+  if (npub > ix->pub.n) {
+    CU_TRY(ix->pub.reserve(npub));
+    CU_TRY(cudaMemsetAsync(ix->pub.p, 0, npub * 8, s));  // epoch 0 is never used by a launch
+  }
+  if (ix->cand_count.n < 2 * kTcQRows) {
+    CU_TRY(ix->cand_count.reserve(2 * kTcQRows));
+    CU_TRY(cudaMemsetAsync(ix->cand_count.p, 0, 2 * kTcQRows * 4, s));
+  }
+  if (++ix->epoch == 0) ix->epoch = 1;
   TcParams p;
   p.q = static_cast<const __nv_bfloat16*>(q_dev);
   p.inv_norm = ix->d_inv_norm;
   p.cand = ix->cand_a.p;
+  p.cand_count = ix->cand_count.p;
   p.dbg_scores = dbg;
+  p.pub = ix->pub.p;
+  p.epoch = ix->epoch;
   p.n_rows = ix->rows;
   p.nq = nqb; p.dim = ix->dim; p.ksel = ksel; p.n_lists = n_lists; p.n_qblocks = n_qblocks;
   p.num_stages = stages;
@@ -205,9 +221,11 @@ int search_dev_locked(aur_index* ix, const void* q_dev, int nq, int k, const int
       ix->last_launches += 1;
       cur = ix->cand_a.p;
     }
-    // fold candidate lists until one sort of <= 4096 keys finishes the job
+    // dense candidate lists (SIMT path): fold until one sort of <= 4096 keys finishes the
+    // job.  The tcgen05 kernel already compacted its survivors per query.
+    const bool compact = kernel != AUR_KERNEL_SIMT;
     bool in_a = true;
-    while (static_cast<int64_t>(n_lists) * ksel > 4096) {
+    while (!compact && static_cast<int64_t>(n_lists) * ksel > 4096) {
       const int group = 4096 / ksel;
       const int n_groups = (n_lists + group - 1) / group;
       DevBuf<uint64_t>& dst = in_a ? ix->cand_b : ix->cand_a;
@@ -219,6 +237,7 @@ int search_dev_locked(aur_index* ix, const void* q_dev, int nq, int k, const int
     }
     FinalizeArgs fa;
     fa.cand = cur; fa.n_lists = n_lists; fa.ksel = ksel;
+    fa.counts = compact ? ix->cand_count.p : nullptr;
     fa.q = qb; fa.rows = ix->d_rows; fa.dtype = ix->dtype; fa.dim = ix->dim; fa.nq = nqb; fa.k = k;
     fa.ids = ix->d_ids;
     fa.out_scores = scores + static_cast<size_t>(q0) * k;
@@ -327,7 +346,7 @@ int aur_close(aur_index* ix) {
   cudaSetDevice(ix->device);
   if (ix->stream) cudaStreamSynchronize(ix->stream);
   cudaFree(ix->d_rows); cudaFree(ix->d_inv_norm); cudaFree(ix->d_ids); cudaFree(ix->d_user); cudaFree(ix->d_org);
-  ix->cand_a.release(); ix->cand_b.release(); ix->score_chunk.release(); ix->stage_q.release();
+  ix->cand_a.release(); ix->cand_b.release(); ix->pub.release(); ix->cand_count.release(); ix->score_chunk.release(); ix->stage_q.release();
   ix->stage_quser.release(); ix->stage_qorg.release(); ix->stage_scores.release(); ix->stage_ids.release();
   ix->dbg.release();
   if (ix->ev_begin) cudaEventDestroy(ix->ev_begin);
@@ -532,6 +551,7 @@ int aur_debug_tc_scores(aur_index* ix, const void* queries_dev, int32_t nq, int3
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ix->stream;
   int rc = run_tc_block(ix, cta_group, queries_dev, nq, 32 + kSlack, out_dev, &n_lists, s);
   if (rc != AUR_OK) return rc;
+  CU_TRY(cudaMemsetAsync(ix->cand_count.p, 0, 2 * kTcQRows * 4, s));  // no finalize ran to reset them
   if (n_ctas_out) *n_ctas_out = ix->sm_count & ~1;
   return AUR_OK;
 }

@@ -49,11 +49,17 @@ constexpr int kMaxK = 128;
 struct TcParams {
   const __nv_bfloat16* q;   // [nq, dim] queries of this launch (<= 128 * n_qblocks)
   const float* inv_norm;    // [n_rows]   1/|c_j|, 0 for zero rows, NaN for tombstones
-  uint64_t* cand;           // [128 * n_qblocks, n_lists, ksel] candidate keys (out)
+  uint64_t* cand;           // [128 * n_qblocks, n_lists * ksel] candidate keys, compacted per
+                            // query: only keys that pass the final threshold are appended
+  uint32_t* cand_count;     // [128 * n_qblocks] appended keys per query (zero on entry)
   float* dbg_scores;        // optional [grid, 128, 64]: first tile's scores of every CTA
+  uint64_t* pub;            // [n_qblocks, n_lists, 128] (epoch << 32 | score bits): each CTA's
+                            // m-th best score per query, the cross-CTA threshold exchange
   int64_t n_rows;
+  uint32_t epoch;           // launch counter: pub entries of older launches are ignored
   int nq, dim, ksel, n_lists, n_qblocks, num_stages, n_tiles;
 };
+constexpr int kTcPubMax = 74;      // published values a thread folds into its threshold
 
 size_t tc_smem_bytes(int cta_group, int num_stages, int ksel);
 int tc_pick_stages(int cta_group, int ksel, size_t smem_limit);
@@ -84,6 +90,8 @@ cudaError_t launch_reduce_lists(const uint64_t* in, int nq, int n_lists, int kse
 // (score desc, id asc) order, top-k out.
 struct FinalizeArgs {
   const uint64_t* cand; int n_lists; int ksel;
+  uint32_t* counts;  // nullable: per-query number of valid keys at the front of its cand row
+                     // (reset to 0 by the kernel); null = all n_lists * ksel slots are keys
   const void* q; const void* rows; int dtype; int dim; int nq; int k;
   const int64_t* ids;
   float* out_scores; int64_t* out_ids; double* out_scores64;

@@ -169,12 +169,27 @@ finalize_kernel(FinalizeArgs a) {
   __shared__ int64_t ex_id[kMaxK + kSlack];
   __shared__ double s_qq;
   const int qi = blockIdx.x;
-  const int n = a.n_lists * a.ksel;
-  int P = 1; while (P < n) P <<= 1;
-  const uint64_t* src = a.cand + static_cast<size_t>(qi) * n;
-  for (int i = threadIdx.x; i < P; i += blockDim.x) skeys[i] = i < n ? src[i] : 0ull;
+  const int cap = a.n_lists * a.ksel;                       // row stride of cand
+  const int n = a.counts ? min(static_cast<int>(a.counts[qi]), cap) : cap;
+  const uint64_t* src = a.cand + static_cast<size_t>(qi) * cap;
+  // Sort in rounds of at most kSortCap keys; the best ksel of earlier rounds ride along
+  // at the front.  (One round unless a compacted row overflows the sort buffer.)
+  int P = 1;
+  {
+    int done = 0, carried = 0;
+    do {
+      const int take = min(n - done, kSortCap - carried);
+      const int m = carried + take;
+      P = 1; while (P < m) P <<= 1;
+      for (int i = carried + threadIdx.x; i < P; i += blockDim.x) skeys[i] = (i < m) ? src[done + i - carried] : 0ull;
+      __syncthreads();
+      bitonic_desc(skeys, P);
+      done += take;
+      carried = min(a.ksel, m);
+    } while (done < n);
+  }
   __syncthreads();
-  bitonic_desc(skeys, P);
+  if (a.counts && threadIdx.x == 0) a.counts[qi] = 0;      // ready for the next launch
 
   const T* rows = static_cast<const T*>(a.rows);
   const T* qv = static_cast<const T*>(a.q) + static_cast<size_t>(qi) * a.dim;
@@ -345,7 +360,10 @@ cudaError_t launch_reduce_lists(const uint64_t* in, int nq, int n_lists, int kse
 
 cudaError_t launch_finalize(const FinalizeArgs& a, cudaStream_t s) {
   int P = 1; while (P < a.n_lists * a.ksel) P <<= 1;
-  if (P > kSortCap) return cudaErrorInvalidValue;
+  if (P > kSortCap) {
+    if (!a.counts) return cudaErrorInvalidValue;   // dense rows must be folded first
+    P = kSortCap;
+  }
   const size_t smem = static_cast<size_t>(P) * 8;
   if (a.dtype == 0) finalize_kernel<__nv_bfloat16><<<a.nq, 512, smem, s>>>(a);
   else finalize_kernel<float><<<a.nq, 512, smem, s>>>(a);

@@ -12,11 +12,18 @@
 //                           128 queries, dim/2 columns), B = corpus tile from smem,
 //                           D = [128 queries x 64 rows] fp32 in one of two TMEM buffers
 //   warps 2-5 epilogue    : thread r owns query r: tcgen05.ld its 64 scores, scale by the
-//                           row's inverse norm, compare against its running k-th best,
-//                           push survivors to a pending list, drain into a k-slot list.
+//                           row's inverse norm, compare against its threshold, push the rare
+//                           survivors to a pending list, drain that into a k-slot list.
 // cta_group::2: a CTA pair shares every corpus tile -- each CTA TMA-loads 32 of the 64
 // rows, the leader issues M=256 MMAs, each CTA's TMEM holds its own 128 queries.
 // cta_group::1: M=128; when nq > 128 two CTAs take the same tiles for the two query halves.
+//
+// Threshold exchange.  A CTA sees only 1/74 of the corpus, so its own k-th best is a loose
+// filter (~270 insertions per query per CTA over 1M rows).  Every CTA therefore publishes,
+// per query, its best (or 2nd best) score so far; a thread periodically reads the values
+// of up to 74 CTAs and takes the R-th largest (R * m >= k + slack): at least k + slack
+// rows with a score >= that value exist somewhere, so nothing below it can reach the final
+// top-k.  This certified global threshold cuts insertions to a handful per query.
 #include <cuda.h>
 #include "internal.h"
 #include "ptx.cuh"
@@ -43,12 +50,84 @@ __host__ __device__ inline SmemLayout make_layout(int cta_group, int num_stages,
   return L;
 }
 
+// Per-thread (= per-query) selection state of the epilogue.
+struct TopkState {
+  uint64_t tau_key;   // smallest key in the full list
+  float tau_local;    // its score (own k-th best)
+  float tau_glob;     // threshold certified by the cross-CTA exchange
+  float tau;          // max of the two: the admission filter
+  int minpos, cnt, nfill;
+};
+
+// Fold this lane's pending candidates into its k-slot list.  Out of line on purpose: it
+// runs a handful of times per query and must stay out of the hot loop's instruction stream.
+// list_a / pend_a: shared addresses of slot 0 for this lane (slot stride 1024 B).
+__device__ __noinline__ TopkState drain_pending(TopkState st, uint32_t list_a, uint32_t pend_a, int ksel) {
+  constexpr uint32_t kStride = kTcQRows * 8u;
+  for (int c = 0; c < st.cnt; ++c) {
+    const uint64_t key = lds_u64(pend_a + c * kStride);
+    bool rescan = false;
+    if (st.nfill < ksel) {             // still filling: append, no scan
+      sts_u64(list_a + st.nfill * kStride, key);
+      rescan = (++st.nfill == ksel);
+    } else if (key > st.tau_key) {     // replace the current minimum
+      sts_u64(list_a + st.minpos * kStride, key);
+      rescan = true;
+    }
+    if (rescan) {
+      uint64_t m = lds_u64(list_a); int mp = 0;
+#pragma unroll 8
+      for (int t = 1; t < ksel; ++t) {
+        const uint64_t v = lds_u64(list_a + t * kStride);
+        if (v < m) { m = v; mp = t; }
+      }
+      st.tau_key = m; st.minpos = mp; st.tau_local = key_score(m);
+    }
+  }
+  st.cnt = 0;
+  st.tau = fmaxf(st.tau_local, st.tau_glob);
+  return st;
+}
+
+// R-th largest of the values published for this query by up to kTcPubMax CTAs (bisection
+// on the value; entries of other launches or not yet written read as NaN and are skipped).
+// Returns -inf when fewer than R CTAs have published.
+__device__ __noinline__ float exchange_threshold(const unsigned long long* pubq, int nuse, int R, uint32_t epoch) {
+  float v[kTcPubMax];
+  float lo = INFINITY, hi = -INFINITY;
+  int nvalid = 0;
+#pragma unroll
+  for (int i = 0; i < kTcPubMax; ++i) {
+    unsigned long long e = 0ull;
+    if (i < nuse) e = __ldcg(pubq + static_cast<size_t>(i) * kTcQRows);
+    const bool ok = static_cast<uint32_t>(e >> 32) == epoch;
+    v[i] = ok ? __uint_as_float(static_cast<uint32_t>(e)) : __int_as_float(0x7FC00000);
+    nvalid += ok ? 1 : 0;
+    lo = fminf(lo, v[i]); hi = fmaxf(hi, v[i]);   // fminf / fmaxf skip NaN
+  }
+  if (nvalid < R) return -INFINITY;
+  // invariant: count(v >= lo) >= R
+#pragma unroll 1
+  for (int round = 0; round < 12; ++round) {
+    const float mid = 0.5f * (lo + hi);
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < kTcPubMax; ++i) c += (v[i] >= mid) ? 1 : 0;
+    if (c >= R) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+constexpr uint32_t kDescHi = 0x40004040u;  // SBO = 1024 B, descriptor version 1, SWIZZLE_128B
+
 template <int kCtaGroup>
 __global__ void __launch_bounds__(kTcThreads, 1)
 simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // SWIZZLE_128B tiles need 1024-byte alignment; the runtime only guarantees 16.
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // SWIZZLE_128B tiles need 1024-byte alignment; the runtime only guarantees 16.  Offsetting
+  // the declared array (rather than round-tripping through an integer) keeps the compiler's
+  // shared-address-space inference, i.e. LDS/STS instead of generic loads.
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
   const SmemLayout L = make_layout(kCtaGroup, p.num_stages, p.ksel);
   uint64_t* list = reinterpret_cast<uint64_t*>(smem + L.off_list);   // [ksel][128]
@@ -131,35 +210,43 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0 && rank == 0) {
+    // The whole warp walks the pipeline (so every operand stays warp-uniform and lives in
+    // uniform registers); one elected lane issues the MMAs and their commits.
+    if (rank == 0) {
       mbar_wait(q_ready, 0);  // queries of (both) CTAs are in TMEM
       tc_fence_after();
       constexpr uint32_t idesc = idesc_bf16_f32(128 * kCtaGroup, kTcTileN);
+      constexpr uint32_t kBox16 = ((kTcTileN / kCtaGroup) * 128u) >> 4;  // box stride in descriptor units
       int stage = 0; uint32_t phase = 0;
       for (int it = 0; it < my_tiles; ++it) {
         const int b = it & 1;
         mbar_wait(&tmem_empty[b], ((static_cast<uint32_t>(it) >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + kTcAccCol0 + b * kTcTileN;
-        uint32_t accumulate = 0;
         for (int kb0 = 0; kb0 < kbs; kb0 += kTcKbPerStage) {
           const int nkb = min(kTcKbPerStage, kbs - kb0);
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sbase = smem_u32(smem + static_cast<uint32_t>(stage) * L.stage_bytes);
-          for (int j = 0; j < nkb; ++j) {
-            const uint64_t desc = smem_desc_sw128(sbase + j * L.box_bytes);
-            const uint32_t a_col = tmem_base + static_cast<uint32_t>(kb0 + j) * 32u;
+          const uint32_t base_lo = (smem_u32(smem + static_cast<uint32_t>(stage) * L.stage_bytes) & 0x3FFFFu) >> 4;
+          const uint32_t a_col = tmem_base + static_cast<uint32_t>(kb0) * 32u;
+          if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {  // 4 x K=16 per 128-byte k-block
-              mma_ts_bf16<kCtaGroup>(d_tmem, a_col + k * 8, desc + static_cast<uint64_t>(k * 2), idesc, accumulate);
-              accumulate = 1;
+            for (int j = 0; j < kTcKbPerStage; ++j) {
+              if (j < nkb) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {  // 4 x K=16 per 128-byte k-block
+                  const uint32_t acc = (j | k) != 0 ? 1u : (kb0 != 0 ? 1u : 0u);
+                  mma_ts_bf16<kCtaGroup>(d_tmem, a_col + j * 32 + k * 8, pack_u64(base_lo + j * kBox16 + k * 2, kDescHi),
+                                         idesc, acc);
+                }
+              }
             }
+            mma_commit<kCtaGroup>(&empty_bar[stage]);  // smem slot free once these MMAs retire
+            if (kb0 + kTcKbPerStage >= kbs) mma_commit<kCtaGroup>(&tmem_full[b]);  // accumulator complete
           }
-          mma_commit<kCtaGroup>(&empty_bar[stage]);  // smem slot free once these MMAs retire
+          __syncwarp();
           if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
         }
-        mma_commit<kCtaGroup>(&tmem_full[b]);  // accumulator complete -> epilogue
       }
     }
   } else {
@@ -193,33 +280,23 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       }
     }
 
-    // ---- 2. running top-k state: list[t][r], t < ksel; the minimum is tracked
-    for (int t = 0; t < p.ksel; ++t) list[t * kTcQRows + r] = kKeyEmpty;
-    uint64_t tau_key = kKeyEmpty;
-    float tau = -INFINITY;
-    int minpos = 0, cnt = 0;
+    // ---- 2. running top-k state: list[t][r], t < ksel; the minimum is tracked once full
+    const int ksel = p.ksel;
+    const uint32_t list_a = smem_u32(list) + r * 8u;   // + t * 1024
+    const uint32_t pend_a = smem_u32(pend) + r * 8u;   // + c * 1024
+    for (int t = 0; t < ksel; ++t) sts_u64(list_a + t * (kTcQRows * 8u), kKeyEmpty);
+    TopkState st;
+    st.tau_key = kKeyEmpty; st.tau_local = -INFINITY; st.tau_glob = -INFINITY; st.tau = -INFINITY;
+    st.minpos = 0; st.cnt = 0; st.nfill = 0;
+    float top1 = -INFINITY, top2 = -INFINITY, published = -INFINITY;
 
-    auto drain = [&]() {
-      int maxc = cnt;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, o));
-      for (int c = 0; c < maxc; ++c) {
-        if (c < cnt) {
-          const uint64_t key = pend[c * kTcQRows + r];
-          if (key > tau_key) {
-            list[minpos * kTcQRows + r] = key;
-            uint64_t m = list[r]; int mp = 0;
-#pragma unroll 4
-            for (int t = 1; t < p.ksel; ++t) {
-              const uint64_t v = list[t * kTcQRows + r];
-              if (v < m) { m = v; mp = t; }
-            }
-            tau_key = m; minpos = mp; tau = key_score(m);
-          }
-        }
-      }
-      cnt = 0;
-    };
+    // exchange geometry: R-th largest of the m-th best of `nuse` CTAs is a valid threshold
+    const int nuse = min(n_lists, kTcPubMax);
+    const int xm = (ksel <= nuse) ? 1 : 2;
+    const int xR = (ksel + xm - 1) / xm;
+    const bool xchg = (p.pub != nullptr) && (xR <= nuse);
+    unsigned long long* pubq =
+        reinterpret_cast<unsigned long long*>(p.pub) + (static_cast<size_t>(qblock) * n_lists) * kTcQRows + r;
 
     // inverse norms of the first tile
     if (my_tiles > 0) {
@@ -237,6 +314,12 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       const int row0 = tile * kTcTileN;
       const int b = it & 1;
       const float* nb = mynorm + b * kTcTileN;
+
+      // ---- threshold exchange (tiles 1..7, then every power of two)
+      if (xchg && it >= 1 && (it < 8 || (it & (it - 1)) == 0)) {
+        st.tau_glob = fmaxf(st.tau_glob, exchange_threshold(pubq, nuse, xR, p.epoch));
+        st.tau = fmaxf(st.tau_local, st.tau_glob);
+      }
 
       mbar_wait(&tmem_full[b], (static_cast<uint32_t>(it) >> 1) & 1u);
       tc_fence_after();
@@ -258,35 +341,80 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         if (rbase + lane + 32 < p.n_rows) nn1 = __ldg(p.inv_norm + rbase + lane + 32);
       }
 
+      // Fast path: scale by 1/|c_j| in place and keep one running max per 16 scores; a
+      // chunk is looked at score by score only if some lane's max reaches its threshold.
+      // (NaN norm = tombstone / out of range: fmaxf drops it and `>=` rejects it.)
+      float cmax[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        if (__any_sync(0xffffffffu, cnt > kTcPendCap - 16)) drain();
+        float m = -INFINITY;
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
           const float4 nv = *reinterpret_cast<const float4*>(nb + c * 16 + j4 * 4);
-          const float nvv[4] = {nv.x, nv.y, nv.z, nv.w};
+          const float s0 = __uint_as_float(acc[c][j4 * 4 + 0]) * nv.x;
+          const float s1 = __uint_as_float(acc[c][j4 * 4 + 1]) * nv.y;
+          const float s2 = __uint_as_float(acc[c][j4 * 4 + 2]) * nv.z;
+          const float s3 = __uint_as_float(acc[c][j4 * 4 + 3]) * nv.w;
+          acc[c][j4 * 4 + 0] = __float_as_uint(s0); acc[c][j4 * 4 + 1] = __float_as_uint(s1);
+          acc[c][j4 * 4 + 2] = __float_as_uint(s2); acc[c][j4 * 4 + 3] = __float_as_uint(s3);
+          m = fmaxf(fmaxf(m, fmaxf(s0, s1)), fmaxf(s2, s3));
+        }
+        cmax[c] = m;
+      }
+      if (p.dbg_scores != nullptr && it == 0) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int col = c * 16 + j4 * 4 + e;
-            const float s = __uint_as_float(acc[c][j4 * 4 + e]) * nvv[e];  // NaN norm => never selected
-            if (p.dbg_scores != nullptr && it == 0)
-              p.dbg_scores[(static_cast<size_t>(blockIdx.x) * kTcQRows + r) * kTcTileN + col] = s;
-            if (s >= tau) {
-              pend[cnt * kTcQRows + r] = make_key(s, row0 + col);
-              ++cnt;
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            p.dbg_scores[(static_cast<size_t>(blockIdx.x) * kTcQRows + r) * kTcTileN + c * 16 + j] =
+                __uint_as_float(acc[c][j]);
+      }
+
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (__any_sync(0xffffffffu, cmax[c] >= st.tau)) {
+          if (__any_sync(0xffffffffu, st.cnt > kTcPendCap - 16)) st = drain_pending(st, list_a, pend_a, ksel);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float s = __uint_as_float(acc[c][j]);
+            if (s >= st.tau) {
+              sts_u64(pend_a + st.cnt * (kTcQRows * 8u), make_key(s, row0 + c * 16 + j));
+              ++st.cnt;
+              if (s > top1) { top2 = top1; top1 = s; } else if (s > top2) top2 = s;
             }
           }
         }
       }
+
+      // publish this CTA's m-th best for the exchange (monotone, so stale reads stay valid)
+      const float pv = (xm == 1) ? top1 : top2;
+      if (xchg && pv > published) {
+        published = pv;
+        __stcg(pubq + static_cast<size_t>(my_list) * kTcQRows,
+               (static_cast<unsigned long long>(p.epoch) << 32) | __float_as_uint(pv));
+      }
+
       float* nnext = mynorm + (b ^ 1) * kTcTileN;
       nnext[lane] = nn0; nnext[lane + 32] = nn1;
       __syncwarp();
     }
-    if (__any_sync(0xffffffffu, cnt > 0)) drain();
+    st = drain_pending(st, list_a, pend_a, ksel);
 
-    // ---- 3. publish this CTA's candidates: cand[q][list][t]
-    uint64_t* out = p.cand + (static_cast<size_t>(qglob) * n_lists + my_list) * p.ksel;
-    for (int t = 0; t < p.ksel; ++t) out[t] = list[t * kTcQRows + r];
+    // ---- 3. append the survivors (score >= the certified threshold) to this query's
+    //         compact candidate row
+    if (xchg && my_tiles > 0) st.tau_glob = fmaxf(st.tau_glob, exchange_threshold(pubq, nuse, xR, p.epoch));
+    {
+      const uint32_t thr = f32_to_ord(st.tau_glob);  // tau_glob only: ties at the threshold are kept
+      const size_t cap = static_cast<size_t>(n_lists) * ksel;
+      uint64_t* out = p.cand + static_cast<size_t>(qglob) * cap;
+      for (int t = 0; t < ksel; ++t) {
+        const uint64_t key = lds_u64(list_a + t * (kTcQRows * 8u));
+        if (key != kKeyEmpty && static_cast<uint32_t>(key >> 32) >= thr) {
+          const uint32_t slot = atomicAdd(p.cand_count + qglob, 1u);
+          out[slot] = key;
+        }
+      }
+    }
   }
 
   // ============================== teardown ==============================
