@@ -90,6 +90,8 @@ struct aur_index {
   int sm_count = 0;
   size_t smem_optin = 0;
   int opt_kernel = AUR_KERNEL_AUTO;
+  int opt_dbg_flags = 0;
+  int opt_epi_groups = 0;        // 0 = auto
   int last_kernel = 0, last_launches = 0;
   DevBuf<uint64_t> cand_a, cand_b;
   DevBuf<uint64_t> pub;          // tcgen05 kernel's cross-CTA threshold exchange
@@ -135,13 +137,17 @@ int run_tc_block(aur_index* ix, int cta_group, const void* q_dev, int nqb, int k
   const int n_qblocks = (nqb > kTcQRows) ? 2 : 1;
   if (cta_group == 2 && n_qblocks != 2) cta_group = 1;  // a pair needs 256 query rows
   int grid = ix->sm_count & ~1;
-  const int n_lists = (cta_group == 2) ? grid / 2 : grid / n_qblocks;
-  const int stages = tc_pick_stages(cta_group, ksel, ix->smem_optin);
+  const int n_tsets = (cta_group == 2) ? grid / 2 : grid / n_qblocks;
+  // two epilogue groups (alternating tiles) whenever their lists leave room for >= 4 pipeline stages
+  int epi_groups = ix->opt_epi_groups;
+  if (epi_groups == 0) epi_groups = tc_pick_stages(cta_group, 2, ksel, ix->smem_optin) >= 4 ? 2 : 1;
+  const int stages = tc_pick_stages(cta_group, epi_groups, ksel, ix->smem_optin);
   if (stages < 2) return fail(AUR_ERR_UNSUPPORTED, "k too large for the tcgen05 path's shared memory");
-  const size_t smem = tc_smem_bytes(cta_group, stages, ksel);
+  const size_t smem = tc_smem_bytes(cta_group, epi_groups, stages, ksel);
+  const int n_lists = n_tsets * epi_groups;   // candidate lists per query
   const size_t ncand = static_cast<size_t>(n_qblocks) * kTcQRows * n_lists * ksel;
   CU_TRY(ix->cand_a.reserve(ncand));
-  const size_t npub = static_cast<size_t>(n_qblocks) * n_lists * kTcQRows;
+  const size_t npub = static_cast<size_t>(n_qblocks) * kTcQRows * (((n_tsets + 1) & ~1) + 1);
   if (npub > ix->pub.n) {
     CU_TRY(ix->pub.reserve(npub));
     CU_TRY(cudaMemsetAsync(ix->pub.p, 0, npub * 8, s));  // epoch 0 is never used by a launch
@@ -162,8 +168,9 @@ int run_tc_block(aur_index* ix, int cta_group, const void* q_dev, int nqb, int k
   p.n_rows = ix->rows;
   p.nq = nqb; p.dim = ix->dim; p.ksel = ksel; p.n_lists = n_lists; p.n_qblocks = n_qblocks;
   p.num_stages = stages;
+  p.dbg_flags = ix->opt_dbg_flags;
   p.n_tiles = static_cast<int>((ix->rows + kTcTileN - 1) / kTcTileN);
-  CU_TRY(tc_launch(cta_group, grid, &ix->tmap[cta_group - 1], p, smem, s));
+  CU_TRY(tc_launch(cta_group, epi_groups, grid, &ix->tmap[cta_group - 1], p, smem, s));
   *n_lists_out = n_lists;
   return AUR_OK;
 }
@@ -382,6 +389,12 @@ int aur_set_option(aur_index* ix, const char* key, int64_t value) {
     ix->opt_kernel = static_cast<int>(value);
     return AUR_OK;
   }
+  if (strcmp(key, "epi_groups") == 0) {
+    if (value < 0 || value > 2) return fail(AUR_ERR_INVALID, "epi_groups must be 0 (auto), 1 or 2");
+    ix->opt_epi_groups = static_cast<int>(value);
+    return AUR_OK;
+  }
+  if (strcmp(key, "dbg_flags") == 0) { ix->opt_dbg_flags = static_cast<int>(value); return AUR_OK; }
   return fail(AUR_ERR_INVALID, "unknown option '%s'", key);
 }
 

@@ -38,8 +38,8 @@ constexpr int kTcTileN = 64;       // corpus rows per tile  (MMA N)
 constexpr int kTcKBlock = 64;      // bf16 per 128-byte swizzled smem row
 constexpr int kTcKbPerStage = 4;   // k-blocks per pipeline stage
 constexpr int kTcQRows = 128;      // queries per CTA (TMEM lanes)
-constexpr int kTcPendCap = 32;     // pending candidates per query between drains
-constexpr int kTcThreads = 192;    // producer warp, MMA warp, 4 epilogue warps
+constexpr int kTcChunk = 16;       // scores examined per threshold test
+constexpr int kTcListMin = 64;     // list slots per query: max(ksel, this) so a whole first tile appends
 constexpr int kTcMaxStages = 8;
 constexpr int kTcMaxDim = 768;     // A operand (queries) must fit 384 TMEM columns
 constexpr int kTcAccCol0 = 384;    // accumulator buffers at TMEM columns 384 / 448
@@ -53,19 +53,24 @@ struct TcParams {
                             // query: only keys that pass the final threshold are appended
   uint32_t* cand_count;     // [128 * n_qblocks] appended keys per query (zero on entry)
   float* dbg_scores;        // optional [grid, 128, 64]: first tile's scores of every CTA
-  uint64_t* pub;            // [n_qblocks, n_lists, 128] (epoch << 32 | score bits): each CTA's
-                            // m-th best score per query, the cross-CTA threshold exchange
+  uint64_t* pub;            // cross-CTA threshold exchange, entries (epoch << 32 | score bits):
+                            // [n_qblocks, 128, n_lists (even)] each CTA's m-th best per query,
+                            // then [n_qblocks, 128] the served thresholds
   int64_t n_rows;
   uint32_t epoch;           // launch counter: pub entries of older launches are ignored
   int nq, dim, ksel, n_lists, n_qblocks, num_stages, n_tiles;
+  int dbg_flags;            // bring-up only: 1 = epilogue skips its work, 2 = no MMAs issued
 };
 constexpr int kTcPubMax = 74;      // published values a thread folds into its threshold
 
-size_t tc_smem_bytes(int cta_group, int num_stages, int ksel);
-int tc_pick_stages(int cta_group, int ksel, size_t smem_limit);
+// epi_groups: 1 = four epilogue warps take every tile; 2 = two sets of four alternate tiles
+// (each set owns one TMEM accumulator buffer and its own candidate lists).
+size_t tc_smem_bytes(int cta_group, int epi_groups, int num_stages, int ksel);
+int tc_pick_stages(int cta_group, int epi_groups, int ksel, size_t smem_limit);
 // Launches the fused similarity + top-k kernel.  tmap: CUtensorMap over the corpus with a
 // {64, 64 / cta_group} box and 128-byte swizzle.
-cudaError_t tc_launch(int cta_group, int grid, const void* tmap, const TcParams& p, size_t smem, cudaStream_t s);
+cudaError_t tc_launch(int cta_group, int epi_groups, int grid, const void* tmap, const TcParams& p, size_t smem,
+                      cudaStream_t s);
 
 // ---------------------------------------------------------------- SIMT kernels
 struct FilterArgs {

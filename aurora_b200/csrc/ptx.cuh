@@ -196,7 +196,7 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
 }
 __device__ __forceinline__ uint64_t pack_u64(uint32_t lo, uint32_t hi) {
   uint64_t d;
-  asm volatile("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
   return d;
 }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major.
@@ -221,6 +221,21 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[
       "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
 
+// Packed fp32x2 multiply (FMUL2 on sm_100): both halves rounded like a scalar mul.rn.
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ void unpack_u64(uint64_t v, uint32_t& lo, uint32_t& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
 __device__ __forceinline__ uint64_t lds_u64(uint32_t addr) {
   uint64_t v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr)); return v;
 }

@@ -1,29 +1,48 @@
 // Fused similarity + top-k for sm_100a: S = Q . C^T on tcgen05 tensor cores with the
 // query block resident in TMEM, the corpus streamed once from HBM by TMA, and a per-query
-// running top-k kept in shared memory by the epilogue warps.
+// candidate list kept in shared memory by the epilogue warps.
 //
 // Replaces the dense leg of collection.query.hybrid(...) / near_text(...) that the
 // reference sends to Weaviate (server/routes/knowledge_base/weaviate_client.py:252-259,
 // server/routes/incident_feedback/weaviate_client.py:286-291).
 //
-// Shape of one CTA (192 threads, persistent, 1 CTA / SM):
-//   warp 0   TMA producer : corpus tiles [64 rows x 256 k] -> smem ring (SWIZZLE_128B)
-//   warp 1   MMA issuer   : tcgen05.mma kind::f16, A = queries from TMEM (128 lanes =
-//                           128 queries, dim/2 columns), B = corpus tile from smem,
-//                           D = [128 queries x 64 rows] fp32 in one of two TMEM buffers
-//   warps 2-5 epilogue    : thread r owns query r: tcgen05.ld its 64 scores, scale by the
-//                           row's inverse norm, compare against its threshold, push the rare
-//                           survivors to a pending list, drain that into a k-slot list.
+// One CTA, persistent, 1 CTA / SM (G = 1 or 2 epilogue groups; 32 * (4G + 3) threads):
+//   warps 1..4G epilogue  : thread r of a group owns query r (TMEM lane r): tcgen05.ld its 64 scores of
+//                           a tile, scale by the rows' inverse norms (FMUL2), keep one max
+//                           per 16 scores and compare it with the query's threshold; only
+//                           the four-score group that reaches it goes to the out-of-line
+//                           push_group4().
+//   warp 0     threshold   : serves the certified global threshold of the one or two queries
+//                           assigned to this CTA (see "Threshold exchange").
+//                           With two groups, group g takes tiles g, g+2, ... (TMEM buffer g):
+//                           two MMA tile-times per tile, so the MMA rarely waits on them.
+//   warp 4G+1  TMA producer: corpus tiles [64 rows x 256 k] -> smem ring (SWIZZLE_128B)
+//   warp 4G+2  MMA issuer  : tcgen05.mma kind::f16, A = queries from TMEM (128 lanes = 128
+//                           queries, dim/2 columns), B = corpus tile from smem, D = [128
+//                           queries x 64 rows] fp32 in one of two TMEM buffers.
+// (The scheduler favours the highest warp id of a sub-partition: the two latency-critical
+// single-thread roles get the top ids, the background threshold warp the bottom one.)
 // cta_group::2: a CTA pair shares every corpus tile -- each CTA TMA-loads 32 of the 64
 // rows, the leader issues M=256 MMAs, each CTA's TMEM holds its own 128 queries.
 // cta_group::1: M=128; when nq > 128 two CTAs take the same tiles for the two query halves.
 //
 // Threshold exchange.  A CTA sees only 1/74 of the corpus, so its own k-th best is a loose
-// filter (~270 insertions per query per CTA over 1M rows).  Every CTA therefore publishes,
-// per query, its best (or 2nd best) score so far; a thread periodically reads the values
-// of up to 74 CTAs and takes the R-th largest (R * m >= k + slack): at least k + slack
-// rows with a score >= that value exist somewhere, so nothing below it can reach the final
-// top-k.  This certified global threshold cuts insertions to a handful per query.
+// filter.  Every epilogue thread therefore publishes its best (or 2nd best) score so far
+// into a [query][CTA] table.  Query q is served by CTA q mod 74: its threshold warp reads
+// the row of q every couple of microseconds, takes the R-th largest entry (R * m >= k +
+// slack) and publishes it: at least k + slack rows with a score >= that value exist
+// somewhere, so nothing below it can reach the final top-k.  Every epilogue thread reads its
+// query's current threshold once per tile.  A query then admits only a handful of rows per
+// CTA over a 1M-row scan.
+//
+// Bootstrap.  On its first tile a thread only publishes the tile's best score and waits for
+// the first certified threshold (all CTAs do this at the same time, ~5 us once), then
+// examines the tile against it: no arbitrary rows ever enter a list.
+//
+// Candidate list.  Append-only, ksel slots per query.  If it fills up it is compacted:
+// entries under the current threshold are dropped, and only if ksel live candidates remain
+// does it fall back to replace-the-minimum.  At the end the survivors are appended to the
+// query's compact row in global memory for the finalize kernel.
 #include <cuda.h>
 #include "internal.h"
 #include "ptx.cuh"
@@ -33,106 +52,153 @@ using namespace ptx;
 
 namespace {
 
+constexpr int kThrWarps = 1;
+constexpr uint32_t kSlot = kTcQRows * 8u;   // byte stride between list slots of one query
+
 struct SmemLayout {
-  uint32_t stage_bytes, box_bytes;
-  uint32_t off_list, off_pend, off_norm, off_bar, total;
+  uint32_t stage_bytes, box_bytes, lcap;
+  uint32_t off_list, off_norm, off_bar, total;
 };
-__host__ __device__ inline SmemLayout make_layout(int cta_group, int num_stages, int ksel) {
+__host__ __device__ inline SmemLayout make_layout(int cta_group, int epi_groups, int num_stages, int ksel) {
   SmemLayout L;
   L.box_bytes = (kTcTileN / cta_group) * 128u;
   L.stage_bytes = L.box_bytes * kTcKbPerStage;
+  L.lcap = static_cast<uint32_t>(ksel);
   uint32_t o = L.stage_bytes * num_stages;
-  L.off_list = o;  o += static_cast<uint32_t>(ksel) * kTcQRows * 8u;
-  L.off_pend = o;  o += kTcPendCap * kTcQRows * 8u;
-  L.off_norm = o;  o += 4u * 2u * kTcTileN * 4u;
-  L.off_bar = o;   o += (2u * kTcMaxStages + 2u + 2u + 1u) * 8u + 16u;
+  L.off_list = o;   o += static_cast<uint32_t>(epi_groups) * L.lcap * kSlot;
+  L.off_norm = o;   o += static_cast<uint32_t>(epi_groups) * 4u * 2u * kTcTileN * 4u;
+  L.off_bar = o;    o += (2u * kTcMaxStages + 2u + 2u + 1u) * 8u + 16u;
   L.total = o;
   return L;
 }
 
 // Per-thread (= per-query) selection state of the epilogue.
 struct TopkState {
-  uint64_t tau_key;   // smallest key in the full list
-  float tau_local;    // its score (own k-th best)
-  float tau_glob;     // threshold certified by the cross-CTA exchange
-  float tau;          // max of the two: the admission filter
-  int minpos, cnt, nfill;
+  uint64_t min_key;   // smallest key, valid when the list holds exactly ksel entries (nfill == ksel)
+  float tau_local;    // its score, else -inf
+  float tau;          // admission filter = max(tau_local, certified global threshold)
+  float top1, top2;   // best two scores this thread has admitted (published for the exchange)
+  int minpos, nfill;
 };
 
-// Fold this lane's pending candidates into its k-slot list.  Out of line on purpose: it
-// runs a handful of times per query and must stay out of the hot loop's instruction stream.
-// list_a / pend_a: shared addresses of slot 0 for this lane (slot stride 1024 B).
-__device__ __noinline__ TopkState drain_pending(TopkState st, uint32_t list_a, uint32_t pend_a, int ksel) {
-  constexpr uint32_t kStride = kTcQRows * 8u;
-  for (int c = 0; c < st.cnt; ++c) {
-    const uint64_t key = lds_u64(pend_a + c * kStride);
-    bool rescan = false;
-    if (st.nfill < ksel) {             // still filling: append, no scan
-      sts_u64(list_a + st.nfill * kStride, key);
-      rescan = (++st.nfill == ksel);
-    } else if (key > st.tau_key) {     // replace the current minimum
-      sts_u64(list_a + st.minpos * kStride, key);
-      rescan = true;
-    }
-    if (rescan) {
-      uint64_t m = lds_u64(list_a); int mp = 0;
+__device__ __forceinline__ void scan_min(uint32_t list_a, int n, uint64_t& m, int& mp) {
+  m = lds_u64(list_a); mp = 0;
 #pragma unroll 8
-      for (int t = 1; t < ksel; ++t) {
-        const uint64_t v = lds_u64(list_a + t * kStride);
-        if (v < m) { m = v; mp = t; }
-      }
-      st.tau_key = m; st.minpos = mp; st.tau_local = key_score(m);
-    }
+  for (int t = 1; t < n; ++t) {
+    const uint64_t v = lds_u64(list_a + t * kSlot);
+    if (v < m) { m = v; mp = t; }
   }
-  st.cnt = 0;
-  st.tau = fmaxf(st.tau_local, st.tau_glob);
+}
+
+// Drop what the threshold has made useless, then cut down to ksel entries.
+__device__ __noinline__ TopkState compact_list(TopkState st, uint32_t list_a, int ksel) {
+  const uint32_t thr = f32_to_ord(st.tau);
+  int w = 0;
+  for (int t = 0; t < st.nfill; ++t) {
+    const uint64_t k = lds_u64(list_a + t * kSlot);
+    if (static_cast<uint32_t>(k >> 32) >= thr) { sts_u64(list_a + w * kSlot, k); ++w; }
+  }
+  st.nfill = w;
+  while (st.nfill > ksel) {  // rare: this CTA owns more than ksel of the current global best
+    uint64_t m; int mp;
+    scan_min(list_a, st.nfill, m, mp);
+    --st.nfill;
+    sts_u64(list_a + mp * kSlot, lds_u64(list_a + st.nfill * kSlot));
+  }
+  if (st.nfill == ksel) {
+    scan_min(list_a, ksel, st.min_key, st.minpos);
+    st.tau_local = key_score(st.min_key);
+    st.tau = fmaxf(st.tau, st.tau_local);
+  }
   return st;
 }
 
-// R-th largest of the values published for this query by up to kTcPubMax CTAs (bisection
-// on the value; entries of other launches or not yet written read as NaN and are skipped).
-// Returns -inf when fewer than R CTAs have published.
-__device__ __noinline__ float exchange_threshold(const unsigned long long* pubq, int nuse, int R, uint32_t epoch) {
-  float v[kTcPubMax];
+// Admit one score into a query's list.
+__device__ __forceinline__ TopkState push_one(TopkState st, float s, int row, uint32_t list_a, int ksel, int lcap) {
+  if (s > st.top1) { st.top2 = st.top1; st.top1 = s; } else if (s > st.top2) st.top2 = s;
+  const uint64_t key = make_key(s, row);
+  if (st.nfill == lcap) st = compact_list(st, list_a, ksel);
+  if (st.nfill < lcap) {
+    sts_u64(list_a + st.nfill * kSlot, key);
+    ++st.nfill;
+  } else if (key > st.min_key) {  // lcap == ksel and the list is full of live candidates
+    sts_u64(list_a + st.minpos * kSlot, key);
+    scan_min(list_a, ksel, st.min_key, st.minpos);
+    st.tau_local = key_score(st.min_key);
+    st.tau = fmaxf(st.tau, st.tau_local);
+  }
+  return st;
+}
+
+// Examine four adjacent scores of one query (their max reached the threshold).  Out of
+// line and small: at warp level some lane needs this about twice per tile, so it has to be
+// cheap and its code has to stay resident next to the hot loop.
+__device__ __noinline__ TopkState push_group4(TopkState st, float s0, float s1, float s2, float s3, int row,
+                                              uint32_t list_a, int ksel) {
+  if (s0 >= st.tau) st = push_one(st, s0, row + 0, list_a, ksel, ksel);   // `>=` also rejects NaN
+  if (s1 >= st.tau) st = push_one(st, s1, row + 1, list_a, ksel, ksel);
+  if (s2 >= st.tau) st = push_one(st, s2, row + 2, list_a, ksel, ksel);
+  if (s3 >= st.tau) st = push_one(st, s3, row + 3, list_a, ksel, ksel);
+  return st;
+}
+
+// Warp-cooperative: R-th largest of the values published for one query by up to 96 CTAs
+// (lane i holds entries i, i+32, i+64; entries of other launches or not yet written are
+// skipped).  Bisection on the value with ballot counts.  Returns -inf when fewer than R CTAs
+// have published.  All lanes return the same value.
+__device__ float exchange_threshold_warp(const unsigned long long* pubrow, int nuse, int R, uint32_t epoch, int lane) {
+  float v[3];
   float lo = INFINITY, hi = -INFINITY;
   int nvalid = 0;
 #pragma unroll
-  for (int i = 0; i < kTcPubMax; ++i) {
+  for (int k = 0; k < 3; ++k) {
+    const int i = lane + 32 * k;
     unsigned long long e = 0ull;
-    if (i < nuse) e = __ldcg(pubq + static_cast<size_t>(i) * kTcQRows);
-    const bool ok = static_cast<uint32_t>(e >> 32) == epoch;
-    v[i] = ok ? __uint_as_float(static_cast<uint32_t>(e)) : __int_as_float(0x7FC00000);
-    nvalid += ok ? 1 : 0;
-    lo = fminf(lo, v[i]); hi = fmaxf(hi, v[i]);   // fminf / fmaxf skip NaN
+    if (i < nuse) e = __ldcg(pubrow + i);
+    const bool ok = (i < nuse) && static_cast<uint32_t>(e >> 32) == epoch;
+    v[k] = ok ? ord_to_f32(static_cast<uint32_t>(e)) : __int_as_float(0x7FC00000);
+    nvalid += __popc(__ballot_sync(0xffffffffu, ok));
+    lo = fminf(lo, v[k]); hi = fmaxf(hi, v[k]);   // fminf / fmaxf skip NaN
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
   }
   if (nvalid < R) return -INFINITY;
   // invariant: count(v >= lo) >= R
-#pragma unroll 1
   for (int round = 0; round < 12; ++round) {
     const float mid = 0.5f * (lo + hi);
     int c = 0;
 #pragma unroll
-    for (int i = 0; i < kTcPubMax; ++i) c += (v[i] >= mid) ? 1 : 0;
+    for (int k = 0; k < 3; ++k) c += __popc(__ballot_sync(0xffffffffu, v[k] >= mid));
     if (c >= R) lo = mid; else hi = mid;
   }
   return lo;
 }
 
-constexpr uint32_t kDescHi = 0x40004040u;  // SBO = 1024 B, descriptor version 1, SWIZZLE_128B
+__device__ __forceinline__ float read_threshold(const unsigned long long* tq, uint32_t epoch) {
+  const unsigned long long e = __ldcg(tq);
+  return (static_cast<uint32_t>(e >> 32) == epoch) ? __uint_as_float(static_cast<uint32_t>(e)) : -INFINITY;
+}
 
-template <int kCtaGroup>
-__global__ void __launch_bounds__(kTcThreads, 1)
+constexpr uint32_t kDescHi = 0x40004040u;  // SBO = 1024 B, descriptor version 1, SWIZZLE_128B
+constexpr uint32_t kNaNBits = 0x7FC00000u;
+
+template <int kCtaGroup, int kEpiGroups>
+__global__ void __launch_bounds__(32 * (4 * kEpiGroups + 3), 1)
 simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
+  constexpr int kEpiWarps = 4 * kEpiGroups;
+  constexpr int kProducerWarp = kEpiWarps + kThrWarps;
+  constexpr int kMmaWarp = kProducerWarp + 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment; the runtime only guarantees 16.  Offsetting
   // the declared array (rather than round-tripping through an integer) keeps the compiler's
   // shared-address-space inference, i.e. LDS/STS instead of generic loads.
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
-  const SmemLayout L = make_layout(kCtaGroup, p.num_stages, p.ksel);
-  uint64_t* list = reinterpret_cast<uint64_t*>(smem + L.off_list);   // [ksel][128]
-  uint64_t* pend = reinterpret_cast<uint64_t*>(smem + L.off_pend);   // [kTcPendCap][128]
-  float* normbuf = reinterpret_cast<float*>(smem + L.off_norm);      // [4][2][64]
+  const SmemLayout L = make_layout(kCtaGroup, kEpiGroups, p.num_stages, p.ksel);
+  float* normbuf = reinterpret_cast<float*>(smem + L.off_norm);      // [4 warps][2][64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);
   uint64_t* full_bar = bars;                              // [kTcMaxStages]
   uint64_t* empty_bar = bars + kTcMaxStages;              // [kTcMaxStages]
@@ -140,40 +206,50 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   uint64_t* tmem_empty = bars + 2 * kTcMaxStages + 2;     // [2]
   uint64_t* q_ready = bars + 2 * kTcMaxStages + 4;        // [1]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kTcMaxStages + 5);
+  volatile int* epi_done = reinterpret_cast<volatile int*>(tmem_ptr_smem + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = (kCtaGroup == 2) ? cluster_ctarank() : 0u;
 
-  // Work split.  list = which set of corpus tiles; qblock = which 128 queries.
-  int qblock, my_list, n_lists;
+  // Work split.  tset = which set of corpus tiles this CTA (pair) walks; qblock = which 128 queries.
+  int qblock, tset, n_tsets;
   if constexpr (kCtaGroup == 2) {
     qblock = static_cast<int>(rank);
-    my_list = blockIdx.x >> 1;
-    n_lists = gridDim.x >> 1;
+    tset = blockIdx.x >> 1;
+    n_tsets = gridDim.x >> 1;
   } else {
     qblock = blockIdx.x % p.n_qblocks;
-    my_list = blockIdx.x / p.n_qblocks;
-    n_lists = gridDim.x / p.n_qblocks;
+    tset = blockIdx.x / p.n_qblocks;
+    n_tsets = gridDim.x / p.n_qblocks;
   }
-  const int my_tiles = (p.n_tiles > my_list) ? (p.n_tiles - my_list + n_lists - 1) / n_lists : 0;
+  const int my_tiles = (p.n_tiles > tset) ? (p.n_tiles - tset + n_tsets - 1) / n_tsets : 0;
   const int kbs = p.dim / kTcKBlock;  // 128-byte k-blocks per row
+
+  // exchange geometry: R-th largest of the m-th best of `nuse` CTAs is a valid threshold
+  const int ksel = p.ksel;
+  const int nuse = min(n_tsets, 96);
+  const int xm = (ksel <= nuse) ? 1 : 2;
+  const int xR = (ksel + xm - 1) / xm;
+  // (only CTAs that own at least one tile ever publish)
+  const bool xchg = (p.pub != nullptr) && (xR <= min(nuse, p.n_tiles));
 
   if constexpr (kCtaGroup == 2) cluster_sync_all();  // both CTAs resident before the paired TMEM alloc
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kMmaWarp && lane == 0) {
     prefetch_tmap(&tmap);
     for (int i = 0; i < p.num_stages; ++i) {
       mbar_init(&full_bar[i], kCtaGroup);  // leader's expect_tx arrive (+ the peer producer's arrive)
       mbar_init(&empty_bar[i], 1);         // one tcgen05.commit
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&tmem_full[i], 1);               // one tcgen05.commit
-      mbar_init(&tmem_empty[i], 4 * kCtaGroup);  // one arrive per epilogue warp (of both CTAs)
+      mbar_init(&tmem_full[i], 1);                       // one tcgen05.commit
+      mbar_init(&tmem_empty[i], 4 * kCtaGroup);          // the four warps (per CTA) that drain this buffer
     }
-    mbar_init(q_ready, 4 * kCtaGroup);
+    mbar_init(q_ready, kEpiWarps * kCtaGroup);
+    *epi_done = 0;
     fence_mbar_init();
-  } else if (warp == 2) {
+  } else if (warp == kProducerWarp) {
     tmem_alloc<kCtaGroup>(tmem_ptr_smem, 512);
     tmem_relinquish<kCtaGroup>();
   }
@@ -182,13 +258,13 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
       const uint64_t hint = (kCtaGroup == 2 || p.n_qblocks == 1) ? kEvictFirst : kEvictNormal;
       int stage = 0; uint32_t phase = 0;
       for (int it = 0; it < my_tiles; ++it) {
-        const int tile = my_list + it * n_lists;
+        const int tile = tset + it * n_tsets;
         const int row0 = tile * kTcTileN + static_cast<int>(rank) * (kTcTileN / kCtaGroup);
         for (int kb0 = 0; kb0 < kbs; kb0 += kTcKbPerStage) {
           const int nkb = min(kTcKbPerStage, kbs - kb0);
@@ -208,7 +284,7 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ============================== MMA issuer ==============================
     // The whole warp walks the pipeline (so every operand stays warp-uniform and lives in
     // uniform registers); one elected lane issues the MMAs and their commits.
@@ -218,21 +294,31 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       constexpr uint32_t idesc = idesc_bf16_f32(128 * kCtaGroup, kTcTileN);
       constexpr uint32_t kBox16 = ((kTcTileN / kCtaGroup) * 128u) >> 4;  // box stride in descriptor units
       int stage = 0; uint32_t phase = 0;
+      long long tm_empty = 0, tm_full = 0;
+      const long long tm_begin = clock64();
       for (int it = 0; it < my_tiles; ++it) {
         const int b = it & 1;
-        mbar_wait(&tmem_empty[b], ((static_cast<uint32_t>(it) >> 1) & 1u) ^ 1u);
+        {
+          const long long t0 = clock64();
+          mbar_wait(&tmem_empty[b], ((static_cast<uint32_t>(it) >> 1) & 1u) ^ 1u);
+          tm_empty += clock64() - t0;
+        }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + kTcAccCol0 + b * kTcTileN;
         for (int kb0 = 0; kb0 < kbs; kb0 += kTcKbPerStage) {
           const int nkb = min(kTcKbPerStage, kbs - kb0);
-          mbar_wait(&full_bar[stage], phase);
+          {
+            const long long t0 = clock64();
+            mbar_wait(&full_bar[stage], phase);
+            tm_full += clock64() - t0;
+          }
           tc_fence_after();
           const uint32_t base_lo = (smem_u32(smem + static_cast<uint32_t>(stage) * L.stage_bytes) & 0x3FFFFu) >> 4;
           const uint32_t a_col = tmem_base + static_cast<uint32_t>(kb0) * 32u;
           if (elect_one()) {
 #pragma unroll
             for (int j = 0; j < kTcKbPerStage; ++j) {
-              if (j < nkb) {
+              if (j < nkb && !(p.dbg_flags & 2)) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {  // 4 x K=16 per 128-byte k-block
                   const uint32_t acc = (j | k) != 0 ? 1u : (kb0 != 0 ? 1u : 0u);
@@ -248,171 +334,261 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
           if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
         }
       }
+      if ((p.dbg_flags & 64) && p.dbg_scores != nullptr && lane == 0) {
+        float* d = p.dbg_scores + static_cast<size_t>(blockIdx.x) * kTcQRows * kTcTileN + 32;
+        d[0] = static_cast<float>(tm_empty); d[1] = static_cast<float>(tm_full);
+        d[2] = static_cast<float>(clock64() - tm_begin);
+      }
     }
   } else {
-    // ============================== epilogue: per-query top-k ==============================
+    // ================= threshold warp (0) and epilogue warps (1-4) =================
     const int quarter = warp & 3;              // TMEM lane quarter this warp may touch
     const int r = quarter * 32 + lane;         // TMEM lane == query row inside the CTA
     const int qglob = qblock * kTcQRows + r;   // query index inside this launch
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    float* mynorm = normbuf + (warp - 2) * 2 * kTcTileN;
+    // exchange table: [qblock][query][CTA] -> a query's row is contiguous (592 B for 74 CTAs);
+    // behind it, one published threshold per query
+    const int pub_stride = (n_tsets + 1) & ~1;
+    unsigned long long* pub_base =
+        reinterpret_cast<unsigned long long*>(p.pub) + static_cast<size_t>(qblock) * kTcQRows * pub_stride;
+    unsigned long long* thr_base = reinterpret_cast<unsigned long long*>(p.pub) +
+                                   static_cast<size_t>(p.n_qblocks) * kTcQRows * pub_stride + qblock * kTcQRows;
+    unsigned long long* pubrow = pub_base + static_cast<size_t>(r) * pub_stride;
+    const unsigned long long* thr_q = thr_base + r;
 
-    // ---- 1. park this thread's query row in TMEM (bf16 pairs, K ascending along columns)
-    {
-      const uint4* src = reinterpret_cast<const uint4*>(p.q + static_cast<size_t>(qglob) * p.dim);
-      for (int kb = 0; kb < kbs; ++kb) {
-        uint32_t v[2][16];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          uint4 x = make_uint4(0, 0, 0, 0);
-          if (qglob < p.nq) x = ldg_nc_v4(src + kb * 8 + i);
-          v[i >> 2][(i & 3) * 4 + 0] = x.x; v[i >> 2][(i & 3) * 4 + 1] = x.y;
-          v[i >> 2][(i & 3) * 4 + 2] = x.z; v[i >> 2][(i & 3) * 4 + 3] = x.w;
-        }
-        tmem_st_x16(lane_addr + kb * 32, v[0]);
-        tmem_st_x16(lane_addr + kb * 32 + 16, v[1]);
-      }
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (kCtaGroup == 2) mbar_arrive_cluster(q_ready, 0); else mbar_arrive(q_ready);
-      }
-    }
-
-    // ---- 2. running top-k state: list[t][r], t < ksel; the minimum is tracked once full
-    const int ksel = p.ksel;
-    const uint32_t list_a = smem_u32(list) + r * 8u;   // + t * 1024
-    const uint32_t pend_a = smem_u32(pend) + r * 8u;   // + c * 1024
-    for (int t = 0; t < ksel; ++t) sts_u64(list_a + t * (kTcQRows * 8u), kKeyEmpty);
-    TopkState st;
-    st.tau_key = kKeyEmpty; st.tau_local = -INFINITY; st.tau_glob = -INFINITY; st.tau = -INFINITY;
-    st.minpos = 0; st.cnt = 0; st.nfill = 0;
-    float top1 = -INFINITY, top2 = -INFINITY, published = -INFINITY;
-
-    // exchange geometry: R-th largest of the m-th best of `nuse` CTAs is a valid threshold
-    const int nuse = min(n_lists, kTcPubMax);
-    const int xm = (ksel <= nuse) ? 1 : 2;
-    const int xR = (ksel + xm - 1) / xm;
-    const bool xchg = (p.pub != nullptr) && (xR <= nuse);
-    unsigned long long* pubq =
-        reinterpret_cast<unsigned long long*>(p.pub) + (static_cast<size_t>(qblock) * n_lists) * kTcQRows + r;
-
-    // inverse norms of the first tile
-    if (my_tiles > 0) {
-      const int64_t rbase = static_cast<int64_t>(my_list) * kTcTileN;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int64_t row = rbase + lane + 32 * h;
-        mynorm[lane + 32 * h] = (row < p.n_rows) ? __ldg(p.inv_norm + row) : __int_as_float(0x7FC00000);
-      }
-      __syncwarp();
-    }
-
-    for (int it = 0; it < my_tiles; ++it) {
-      const int tile = my_list + it * n_lists;
-      const int row0 = tile * kTcTileN;
-      const int b = it & 1;
-      const float* nb = mynorm + b * kTcTileN;
-
-      // ---- threshold exchange (tiles 1..7, then every power of two)
-      if (xchg && it >= 1 && (it < 8 || (it & (it - 1)) == 0)) {
-        st.tau_glob = fmaxf(st.tau_glob, exchange_threshold(pubq, nuse, xR, p.epoch));
-        st.tau = fmaxf(st.tau_local, st.tau_glob);
-      }
-
-      mbar_wait(&tmem_full[b], (static_cast<uint32_t>(it) >> 1) & 1u);
-      tc_fence_after();
-      uint32_t acc[4][16];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_x16(lane_addr + kTcAccCol0 + b * kTcTileN + c * 16, acc[c]);
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {  // accumulator drained into registers: hand the buffer back to the MMA warp
-        if constexpr (kCtaGroup == 2) mbar_arrive_cluster(&tmem_empty[b], 0); else mbar_arrive(&tmem_empty[b]);
-      }
-
-      // prefetch the next tile's inverse norms (latency hidden behind this tile's work)
-      float nn0 = __int_as_float(0x7FC00000), nn1 = nn0;
-      if (it + 1 < my_tiles) {
-        const int64_t rbase = static_cast<int64_t>(tile + n_lists) * kTcTileN;
-        if (rbase + lane < p.n_rows) nn0 = __ldg(p.inv_norm + rbase + lane);
-        if (rbase + lane + 32 < p.n_rows) nn1 = __ldg(p.inv_norm + rbase + lane + 32);
-      }
-
-      // Fast path: scale by 1/|c_j| in place and keep one running max per 16 scores; a
-      // chunk is looked at score by score only if some lane's max reaches its threshold.
-      // (NaN norm = tombstone / out of range: fmaxf drops it and `>=` rejects it.)
-      float cmax[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float m = -INFINITY;
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 nv = *reinterpret_cast<const float4*>(nb + c * 16 + j4 * 4);
-          const float s0 = __uint_as_float(acc[c][j4 * 4 + 0]) * nv.x;
-          const float s1 = __uint_as_float(acc[c][j4 * 4 + 1]) * nv.y;
-          const float s2 = __uint_as_float(acc[c][j4 * 4 + 2]) * nv.z;
-          const float s3 = __uint_as_float(acc[c][j4 * 4 + 3]) * nv.w;
-          acc[c][j4 * 4 + 0] = __float_as_uint(s0); acc[c][j4 * 4 + 1] = __float_as_uint(s1);
-          acc[c][j4 * 4 + 2] = __float_as_uint(s2); acc[c][j4 * 4 + 3] = __float_as_uint(s3);
-          m = fmaxf(fmaxf(m, fmaxf(s0, s1)), fmaxf(s2, s3));
-        }
-        cmax[c] = m;
-      }
-      if (p.dbg_scores != nullptr && it == 0) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            p.dbg_scores[(static_cast<size_t>(blockIdx.x) * kTcQRows + r) * kTcTileN + c * 16 + j] =
-                __uint_as_float(acc[c][j]);
-      }
-
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (__any_sync(0xffffffffu, cmax[c] >= st.tau)) {
-          if (__any_sync(0xffffffffu, st.cnt > kTcPendCap - 16)) st = drain_pending(st, list_a, pend_a, ksel);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float s = __uint_as_float(acc[c][j]);
-            if (s >= st.tau) {
-              sts_u64(pend_a + st.cnt * (kTcQRows * 8u), make_key(s, row0 + c * 16 + j));
-              ++st.cnt;
-              if (s > top1) { top2 = top1; top1 = s; } else if (s > top2) top2 = s;
-            }
+    if (warp < kThrWarps) {
+      // ============================== threshold warp ==============================
+      // Serve the queries r = tset, tset + n_tsets, ... of this CTA's query block.
+      float cur[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      while (xchg && my_tiles > 0) {
+        __nanosleep(1500);
+        const bool done = *epi_done >= kEpiWarps;
+        int slot = 0;
+        for (int rq = tset; rq < kTcQRows && slot < 4; rq += n_tsets, ++slot) {
+          const float t = exchange_threshold_warp(pub_base + static_cast<size_t>(rq) * pub_stride, nuse, xR, p.epoch, lane);
+          if (t > cur[slot]) {
+            cur[slot] = t;
+            if (lane == 0) __stcg(thr_base + rq, (static_cast<unsigned long long>(p.epoch) << 32) | __float_as_uint(t));
           }
         }
+        if (done) break;
       }
-
-      // publish this CTA's m-th best for the exchange (monotone, so stale reads stay valid)
-      const float pv = (xm == 1) ? top1 : top2;
-      if (xchg && pv > published) {
-        published = pv;
-        __stcg(pubq + static_cast<size_t>(my_list) * kTcQRows,
-               (static_cast<unsigned long long>(p.epoch) << 32) | __float_as_uint(pv));
-      }
-
-      float* nnext = mynorm + (b ^ 1) * kTcTileN;
-      nnext[lane] = nn0; nnext[lane + 32] = nn1;
-      __syncwarp();
-    }
-    st = drain_pending(st, list_a, pend_a, ksel);
-
-    // ---- 3. append the survivors (score >= the certified threshold) to this query's
-    //         compact candidate row
-    if (xchg && my_tiles > 0) st.tau_glob = fmaxf(st.tau_glob, exchange_threshold(pubq, nuse, xR, p.epoch));
-    {
-      const uint32_t thr = f32_to_ord(st.tau_glob);  // tau_glob only: ties at the threshold are kept
-      const size_t cap = static_cast<size_t>(n_lists) * ksel;
-      uint64_t* out = p.cand + static_cast<size_t>(qglob) * cap;
-      for (int t = 0; t < ksel; ++t) {
-        const uint64_t key = lds_u64(list_a + t * (kTcQRows * 8u));
-        if (key != kKeyEmpty && static_cast<uint32_t>(key >> 32) >= thr) {
-          const uint32_t slot = atomicAdd(p.cand_count + qglob, 1u);
-          out[slot] = key;
+    } else {
+      // ============================== epilogue warps ==============================
+      const int grp = (warp - kThrWarps) >> 2;   // epilogue group: takes tiles grp, grp + groups, ...
+      const long long t_kernel0 = clock64();
+      // ---- park this thread's query row in TMEM (bf16 pairs, K ascending along columns);
+      //      with two groups each loads every other k-block
+      {
+        const uint4* src = reinterpret_cast<const uint4*>(p.q + static_cast<size_t>(qglob) * p.dim);
+        for (int kb = grp; kb < kbs; kb += kEpiGroups) {
+          uint32_t v[2][16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint4 x = make_uint4(0, 0, 0, 0);
+            if (qglob < p.nq) x = ldg_nc_v4(src + kb * 8 + i);
+            v[i >> 2][(i & 3) * 4 + 0] = x.x; v[i >> 2][(i & 3) * 4 + 1] = x.y;
+            v[i >> 2][(i & 3) * 4 + 2] = x.z; v[i >> 2][(i & 3) * 4 + 3] = x.w;
+          }
+          tmem_st_x16(lane_addr + kb * 32, v[0]);
+          tmem_st_x16(lane_addr + kb * 32 + 16, v[1]);
         }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (kCtaGroup == 2) mbar_arrive_cluster(q_ready, 0); else mbar_arrive(q_ready);
+        }
+      }
+      float* mynorm = normbuf + (warp - kThrWarps) * 2 * kTcTileN;
+      const uint32_t list_a = smem_u32(smem + L.off_list) + (static_cast<uint32_t>(grp) * L.lcap * kTcQRows + r) * 8u;
+      TopkState st;
+      st.min_key = kKeyEmpty; st.tau_local = -INFINITY; st.tau = -INFINITY;
+      st.top1 = -INFINITY; st.top2 = -INFINITY; st.minpos = 0; st.nfill = 0;
+      float published = -INFINITY;
+      int nslow = 0;
+      long long t_wait = 0, t_slow = 0, t_ld = 0, t_top = 0, t_fast = 0, t_chunks = 0, t_pub = 0;
+      const long long t_begin = clock64();
+      long long t_boot = 0, t_loop_end = 0;
+
+      // inverse norms: tile(0) into buffer 0, tile(1) in flight in registers
+      auto load_norms = [&](int li2, float& a, float& b2) {
+        a = __uint_as_float(kNaNBits); b2 = a;
+        const int it2 = grp + li2 * kEpiGroups;
+        if (it2 < my_tiles) {
+          const int64_t rbase = static_cast<int64_t>(tset + it2 * n_tsets) * kTcTileN;
+          if (rbase + lane < p.n_rows) a = __ldg(p.inv_norm + rbase + lane);
+          if (rbase + lane + 32 < p.n_rows) b2 = __ldg(p.inv_norm + rbase + lane + 32);
+        }
+      };
+      float nn0, nn1;
+      load_norms(0, nn0, nn1);
+      mynorm[lane] = nn0; mynorm[lane + 32] = nn1;
+      load_norms(1, nn0, nn1);
+      __syncwarp();
+
+      // Bootstrap on the first tile: nobody has a threshold yet, and pushing 64 arbitrary rows
+      // through the list would be all waste.  Read the tile once just for its best score(s),
+      // publish them, wait until enough CTAs have done the same (~5 us, once), and let the
+      // main loop examine the tile against the first certified threshold.  The accumulator
+      // is not released here, so the MMA cannot overwrite it before the loop reads it again.
+      if (xchg && grp < my_tiles) {
+        mbar_wait(&tmem_full[grp & 1], 0);
+        tc_fence_after();
+        float t1 = -INFINITY, t2 = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t a16[16];
+          tmem_ld_x16(lane_addr + kTcAccCol0 + (grp & 1) * kTcTileN + c * 16, a16);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float sc = __uint_as_float(a16[j]) * mynorm[c * 16 + j];
+            if (sc > t1) { t2 = t1; t1 = sc; } else if (sc > t2) t2 = sc;
+          }
+        }
+        const float pv0 = (xm == 1) ? t1 : t2;
+        if (pv0 > -INFINITY) {
+          published = pv0;
+          atomicMax(pubrow + tset, (static_cast<unsigned long long>(p.epoch) << 32) | f32_to_ord(pv0));
+        }
+        st.top1 = t1; st.top2 = t2;
+        const long long tb = clock64();
+        float tboot = -INFINITY;
+        do {
+          __nanosleep(300);
+          tboot = read_threshold(thr_q, p.epoch);
+        } while (__any_sync(0xffffffffu, tboot == -INFINITY) && clock64() - tb < 100000);
+        st.tau = fmaxf(st.tau, tboot);
+        t_boot = clock64() - t_begin;
+      }
+
+      int li = 0;  // this group's iteration count
+      for (int it = grp; it < my_tiles; it += kEpiGroups, ++li) {
+        const int tile = tset + it * n_tsets;
+        const int row0 = tile * kTcTileN;
+        const int b = it & 1;
+        const float* nb = mynorm + (li & 1) * kTcTileN;
+        const long long t_top0 = clock64();
+        const unsigned long long thr_e = xchg ? __ldcg(thr_q) : 0ull;   // consumed after the fast path
+
+        // norms of the next tile (loaded one iteration ago) -> the other buffer; start the
+        // loads for the tile after that.  A whole tile period hides the HBM latency.
+        {
+          float* nnext = mynorm + ((li + 1) & 1) * kTcTileN;
+          nnext[lane] = nn0; nnext[lane + 32] = nn1;
+          load_norms(li + 2, nn0, nn1);
+          __syncwarp();
+        }
+
+        {
+          const long long t0 = clock64();
+          mbar_wait(&tmem_full[b], (static_cast<uint32_t>(it) >> 1) & 1u);
+          t_wait += clock64() - t0;
+        }
+        tc_fence_after();
+        const long long t_ld0 = clock64();
+        uint32_t acc[4][16];
+        if (!(p.dbg_flags & 1)) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tmem_ld_x16(lane_addr + kTcAccCol0 + b * kTcTileN + c * 16, acc[c]);
+          tmem_wait_ld();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {  // accumulator drained into registers: hand the buffer back to the MMA warp
+          if constexpr (kCtaGroup == 2) mbar_arrive_cluster(&tmem_empty[b], 0); else mbar_arrive(&tmem_empty[b]);
+        }
+        t_ld += clock64() - t_ld0;
+        if (p.dbg_flags & 1) continue;
+        const long long t_fast0 = clock64();
+
+        // Fast path: scale by 1/|c_j| in place (packed FMUL2) and keep one running max per 16
+        // scores.  (NaN norm = tombstone / out of range: fmaxf drops it, `>=` rejects it.)
+        float cmax[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float m = -INFINITY;
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const ulonglong2 nv = *reinterpret_cast<const ulonglong2*>(nb + c * 16 + j4 * 4);
+            const uint64_t p0 = mul_f32x2(pack_u64(acc[c][j4 * 4 + 0], acc[c][j4 * 4 + 1]), nv.x);
+            const uint64_t p1 = mul_f32x2(pack_u64(acc[c][j4 * 4 + 2], acc[c][j4 * 4 + 3]), nv.y);
+            unpack_u64(p0, acc[c][j4 * 4 + 0], acc[c][j4 * 4 + 1]);
+            unpack_u64(p1, acc[c][j4 * 4 + 2], acc[c][j4 * 4 + 3]);
+            m = fmaxf(fmaxf(m, fmaxf(__uint_as_float(acc[c][j4 * 4 + 0]), __uint_as_float(acc[c][j4 * 4 + 1]))),
+                      fmaxf(__uint_as_float(acc[c][j4 * 4 + 2]), __uint_as_float(acc[c][j4 * 4 + 3])));
+          }
+          cmax[c] = m;
+        }
+        if (p.dbg_scores != nullptr && it == 0 && !(p.dbg_flags & 64)) {  // (group 0 owns tile 0)
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              p.dbg_scores[(static_cast<size_t>(blockIdx.x) * kTcQRows + r) * kTcTileN + c * 16 + j] =
+                  __uint_as_float(acc[c][j]);
+        }
+
+        t_fast += clock64() - t_fast0;
+        const long long t_ch0 = clock64();
+        // A group of four scores whose max reaches this query's threshold goes out of line.
+        if (static_cast<uint32_t>(thr_e >> 32) == p.epoch) st.tau = fmaxf(st.tau, __uint_as_float(static_cast<uint32_t>(thr_e)));
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (cmax[c] >= st.tau) {
+            const long long t0 = clock64();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float s0 = __uint_as_float(acc[c][4 * g]), s1 = __uint_as_float(acc[c][4 * g + 1]);
+              const float s2 = __uint_as_float(acc[c][4 * g + 2]), s3 = __uint_as_float(acc[c][4 * g + 3]);
+              if (fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)) >= st.tau)
+                st = push_group4(st, s0, s1, s2, s3, row0 + c * 16 + 4 * g, list_a, ksel);
+            }
+            ++nslow;
+            t_slow += clock64() - t0;
+          }
+        }
+
+        if (li < 8) t_top += clock64() - t_ch0; else t_chunks += clock64() - t_ch0;   // t_top reused: early tiles
+        const long long t_pub0 = clock64();
+        // publish this CTA's m-th best for the exchange (monotone, so stale reads stay valid)
+        const float pv = (xm == 1) ? st.top1 : st.top2;
+        if (xchg && pv > published) {
+          published = pv;
+          atomicMax(pubrow + tset, (static_cast<unsigned long long>(p.epoch) << 32) | f32_to_ord(pv));
+        }
+        t_pub += clock64() - t_pub0;
+      }
+      t_loop_end = clock64();
+      __syncwarp();
+      if (lane == 0) atomicAdd(const_cast<int*>(epi_done), 1);   // lets the threshold warps go
+
+      // ---- append the survivors (score >= the certified threshold, at most ksel of them)
+      //      to this query's compact candidate row
+      float tau_end = -INFINITY;
+      if (xchg && my_tiles > 0) tau_end = read_threshold(thr_q, p.epoch);
+      st.tau = fmaxf(st.tau, tau_end);
+      st = compact_list(st, list_a, ksel);
+      {
+        const size_t cap = static_cast<size_t>(n_tsets) * kEpiGroups * ksel;
+        uint64_t* out = p.cand + static_cast<size_t>(qglob) * cap;
+        if (st.nfill > 0) {
+          const uint32_t slot0 = atomicAdd(p.cand_count + qglob, static_cast<uint32_t>(st.nfill));
+          for (int t = 0; t < st.nfill; ++t) out[slot0 + t] = lds_u64(list_a + t * kSlot);
+        }
+      }
+      if ((p.dbg_flags & 64) && p.dbg_scores != nullptr && grp == 0) {
+        float* d = p.dbg_scores + (static_cast<size_t>(blockIdx.x) * kTcQRows + r) * kTcTileN;
+        d[0] = static_cast<float>(st.nfill); d[1] = static_cast<float>(nslow);
+        d[2] = tau_end; d[3] = st.tau_local;
+        d[8] = static_cast<float>(t_wait); d[9] = static_cast<float>(t_slow);
+        d[10] = 0.f; d[11] = static_cast<float>(t_ld);
+        d[12] = static_cast<float>(clock64() - t_begin);
+        d[13] = static_cast<float>(t_top); d[14] = static_cast<float>(t_fast);
+        d[15] = static_cast<float>(t_chunks); d[16] = static_cast<float>(t_pub);
+        d[17] = static_cast<float>(t_boot); d[18] = static_cast<float>(t_begin - t_kernel0);
+        d[19] = static_cast<float>(clock64() - t_loop_end);
       }
     }
   }
@@ -422,25 +598,34 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   tc_fence_before();
   if constexpr (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
-  if (warp == 2) tmem_dealloc<kCtaGroup>(tmem_base, 512);
+  if (warp == kProducerWarp) tmem_dealloc<kCtaGroup>(tmem_base, 512);
+}
+
+template <int kCtaGroup, int kEpiGroups>
+cudaError_t launch_variant(const cudaLaunchConfig_t& cfg, const CUtensorMap& tm, const TcParams& p, size_t smem) {
+  auto kern = simtopk_tc_kernel<kCtaGroup, kEpiGroups>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  return cudaLaunchKernelEx(&cfg, kern, tm, p);
 }
 
 }  // namespace
 
-size_t tc_smem_bytes(int cta_group, int num_stages, int ksel) {
-  return make_layout(cta_group, num_stages, ksel).total + 1024;  // + alignment slack
+size_t tc_smem_bytes(int cta_group, int epi_groups, int num_stages, int ksel) {
+  return make_layout(cta_group, epi_groups, num_stages, ksel).total + 1024;  // + alignment slack
 }
 
-int tc_pick_stages(int cta_group, int ksel, size_t smem_limit) {
+int tc_pick_stages(int cta_group, int epi_groups, int ksel, size_t smem_limit) {
   for (int s = kTcMaxStages; s >= 2; --s)
-    if (tc_smem_bytes(cta_group, s, ksel) <= smem_limit) return s;
+    if (tc_smem_bytes(cta_group, epi_groups, s, ksel) <= smem_limit) return s;
   return 0;
 }
 
-cudaError_t tc_launch(int cta_group, int grid, const void* tmap, const TcParams& p, size_t smem, cudaStream_t s) {
+cudaError_t tc_launch(int cta_group, int epi_groups, int grid, const void* tmap, const TcParams& p, size_t smem,
+                      cudaStream_t s) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kTcThreads);
+  cfg.blockDim = dim3(32 * (4 * epi_groups + 3));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -451,15 +636,8 @@ cudaError_t tc_launch(int cta_group, int grid, const void* tmap, const TcParams&
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const CUtensorMap& tm = *reinterpret_cast<const CUtensorMap*>(tmap);
-  cudaError_t e;
-  if (cta_group == 2) {
-    e = cudaFuncSetAttribute(simtopk_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return e;
-    return cudaLaunchKernelEx(&cfg, simtopk_tc_kernel<2>, tm, p);
-  }
-  e = cudaFuncSetAttribute(simtopk_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  if (e != cudaSuccess) return e;
-  return cudaLaunchKernelEx(&cfg, simtopk_tc_kernel<1>, tm, p);
+  if (cta_group == 2) return epi_groups == 2 ? launch_variant<2, 2>(cfg, tm, p, smem) : launch_variant<2, 1>(cfg, tm, p, smem);
+  return epi_groups == 2 ? launch_variant<1, 2>(cfg, tm, p, smem) : launch_variant<1, 1>(cfg, tm, p, smem);
 }
 
 }  // namespace aur

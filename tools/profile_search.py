@@ -34,6 +34,11 @@ def main():
             # rotate the block so rows differ across chunks without regenerating randn
             ix.add(np.roll(block[:m], lo // block.shape[0], axis=1), np.arange(lo, lo + m, dtype=np.int64))
         ix.set_kernel(kern)
+        flags = int(os.environ.get("AUR_DBG_FLAGS", "0"))
+        if flags:
+            N.check(ix._lib.aur_set_option(ix._h, b"dbg_flags", flags))
+        if os.environ.get("AUR_EPI_GROUPS"):
+            N.check(ix._lib.aur_set_option(ix._h, b"epi_groups", int(os.environ["AUR_EPI_GROUPS"])))
         dq = DeviceBuffer(q.nbytes).upload(q)
         ds = DeviceBuffer(nq * k * 4)
         di = DeviceBuffer(nq * k * 8)
