@@ -475,13 +475,11 @@ int aur_search(aur_index* ix, const void* queries_host, int32_t nq, int32_t k, c
   }
   int rc = search_dev_locked(ix, ix->stage_q.p, nq, k, du, dorg, ix->stage_scores.p, ix->stage_ids.p, nullptr, s);
   if (rc != AUR_OK) return rc;
-  // results land in caller memory only after the whole search succeeded
-  std::vector<float> hs(nout); std::vector<int64_t> hi(nout);
-  CU_TRY(cudaMemcpyAsync(hs.data(), ix->stage_scores.p, nout * 4, cudaMemcpyDeviceToHost, s));
-  CU_TRY(cudaMemcpyAsync(hi.data(), ix->stage_ids.p, nout * 8, cudaMemcpyDeviceToHost, s));
+  // straight into the caller's buffers (async when they are pinned); nothing is written
+  // unless every kernel above was enqueued successfully
+  CU_TRY(cudaMemcpyAsync(scores_out, ix->stage_scores.p, nout * 4, cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaMemcpyAsync(ids_out, ix->stage_ids.p, nout * 8, cudaMemcpyDeviceToHost, s));
   CU_TRY(cudaStreamSynchronize(s));
-  memcpy(scores_out, hs.data(), nout * 4);
-  memcpy(ids_out, hi.data(), nout * 8);
   return AUR_OK;
 }
 

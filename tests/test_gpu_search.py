@@ -1,0 +1,248 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs -- ids bit-exact, scores within 1e-3 (BASELINE.json north_star tolerance; in
+practice they agree to fp32 rounding because the final ranking is an fp64 re-score).
+Run on the B200 box:  python -m pytest tests -m gpu"""
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+from aurora_b200 import _native as N
+from aurora_b200.engine import DeviceBuffer, Index, cosine_pairs, merge_topk_dev, to_bf16_bits
+from oracle import cosine_topk as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "cosine_ref.json")
+
+
+def _data(n, d, nq, seed, bf16=True, planted=4):
+    rng = np.random.default_rng(seed)
+    C = rng.standard_normal((n, d)).astype(np.float32)
+    Q = rng.standard_normal((nq, d)).astype(np.float32)
+    if planted and n >= 8 * nq:
+        for i in range(nq):
+            rows = rng.choice(n, size=planted, replace=False)
+            C[rows] = Q[i][None, :] + 0.3 * rng.standard_normal((planted, d)).astype(np.float32)
+    if bf16:
+        C, Q = O.round_to_bf16(C), O.round_to_bf16(Q)
+    return C, Q
+
+
+def _check(ids, sc, oids, osc):
+    assert np.array_equal(ids, oids), f"{int((ids != oids).sum())} id mismatches"
+    fin = np.isfinite(osc)
+    assert np.array_equal(np.isfinite(sc), fin)
+    if fin.any():
+        assert float(np.max(np.abs(sc[fin] - osc[fin]))) <= TOL
+
+
+def test_library_loaded_and_device_present():
+    assert N.load().aur_device_count() >= 1
+
+
+# ------------------------------------------------------------------ BASELINE config 1 (fp32)
+def test_cfg1_fp32_matches_reference_golden():
+    g = json.load(open(GOLDEN))["cfg1"]
+    C = np.random.default_rng(g["corpus_seed"]).standard_normal((g["N"], g["D"])).astype(np.float32)
+    Q = np.random.default_rng(g["query_seed"]).standard_normal((1, g["D"])).astype(np.float32)
+    with Index(g["D"], g["N"], dtype="f32") as ix:
+        ix.add(C, np.arange(g["N"], dtype=np.int64))
+        ids, sc = ix.search(Q, g["k"])
+        assert ix.stats()["last_kernel"] == N.KERNEL_SIMT
+    assert ids[0].tolist() == g["raw_ids"]                         # produced by the real reference function
+    assert np.allclose(sc[0], g["raw_scores"], atol=1e-6)
+
+
+# ------------------------------------------------------------------ generic (SIMT) path
+@pytest.mark.parametrize("n,d,nq,k,dtype", [
+    (1000, 384, 1, 5, "f32"), (5000, 768, 33, 32, "bf16"), (700, 100, 7, 10, "f32"), (3, 64, 2, 5, "bf16"),
+    (4097, 200, 65, 128, "bf16"), (2048, 8, 3, 1, "bf16"),
+])
+def test_simt_parity(n, d, nq, k, dtype):
+    C, Q = _data(n, d, nq, seed=n + d, bf16=(dtype == "bf16"))
+    ext = np.arange(n, dtype=np.int64) * 3 + 7
+    with Index(d, max(n, 64), dtype=dtype) as ix:
+        ix.set_kernel(N.KERNEL_SIMT)
+        ix.add(C, ext)
+        ids, sc = ix.search(Q, k)
+    _check(ids, sc, *O.cosine_topk(Q, C, k, ids=ext))
+
+
+def test_simt_tenant_filter_and_tombstones():
+    n, d, nq, k = 4000, 128, 9, 8
+    C, Q = _data(n, d, nq, seed=5)
+    rng = np.random.default_rng(9)
+    ru, ro = rng.integers(0, 5, n).astype(np.int32), rng.integers(-1, 3, n).astype(np.int32)
+    qu, qo = rng.integers(0, 5, nq).astype(np.int32), rng.integers(-1, 3, nq).astype(np.int32)
+    live = np.ones(n, dtype=bool)
+    with Index(d, n + 100) as ix:
+        ix.add(C, np.arange(n, dtype=np.int64), ru, ro)
+        dead = rng.choice(n, size=500, replace=False)
+        assert ix.remove(dead) == 500
+        assert ix.remove(dead[:10]) == 0
+        live[dead] = False
+        ids, sc = ix.search(Q, k, qu, qo)                       # filtered => generic path
+        st = ix.stats()
+    assert st["last_kernel"] == N.KERNEL_SIMT and st["live"] == n - 500 and st["rows"] == n
+    _check(ids, sc, *O.cosine_topk(Q, C, k, live=live, row_user=ru, row_org=ro, q_user=qu, q_org=qo))
+
+
+# ------------------------------------------------------------------ tcgen05 path
+@pytest.mark.parametrize("kernel", [N.KERNEL_TC1, N.KERNEL_TC2])
+@pytest.mark.parametrize("n,d,nq,k", [
+    (30000, 768, 256, 32), (9000, 384, 100, 10), (50001, 512, 200, 100), (20000, 768, 300, 5),
+    (777, 64, 1, 1), (12345, 256, 129, 128), (64, 768, 256, 32), (5000, 768, 128, 64),
+])
+def test_tcgen05_parity(kernel, n, d, nq, k):
+    C, Q = _data(n, d, nq, seed=n % 1000 + nq + d)
+    with Index(d, n) as ix:
+        ix.add(C, np.arange(n, dtype=np.int64))
+        ix.set_kernel(kernel)
+        ids, sc = ix.search(Q, k)
+        assert ix.stats()["last_kernel"] == kernel
+    _check(ids, sc, *O.cosine_topk(Q, C, k))
+
+
+@pytest.mark.parametrize("kernel", [N.KERNEL_TC1, N.KERNEL_TC2])
+def test_tcgen05_duplicates_zero_rows_tombstones_upserts(kernel):
+    n, d, nq, k = 20000, 768, 256, 32
+    C, Q = _data(n, d, nq, seed=77)
+    C[1000:1040] = C[999]                       # 41 bit-identical rows: ties broken by id
+    C[5000:5010] = 0.0                          # zero-norm rows score 0.0
+    C[7] = Q[3]                                 # exact match: cosine 1
+    ids0 = np.arange(n, dtype=np.int64)
+    live = np.ones(n, dtype=bool)
+    with Index(d, n + 64) as ix:
+        ix.add(C, ids0)
+        gone = np.array([7, 1003, 15000], dtype=np.int64)
+        assert ix.remove(gone) == 3
+        live[gone] = False
+        ix.set_kernel(kernel)
+        ids, sc = ix.search(Q, k)
+        _check(ids, sc, *O.cosine_topk(Q, C, k, ids=ids0, live=live))
+        # upsert: id 42 gets a new vector; the old row must never come back
+        newv = O.round_to_bf16((Q[5] * 2.0)[None, :])
+        ix.add(newv, np.array([42], dtype=np.int64))
+        ids, sc = ix.search(Q, k)
+    C2 = np.concatenate([C, newv])
+    ids2 = np.concatenate([ids0, [42]])
+    live2 = np.concatenate([live, [True]])
+    live2[42] = False
+    _check(ids, sc, *O.cosine_topk(Q, C2, k, ids=ids2, live=live2))
+    assert ids[5, 0] == 42 and abs(sc[5, 0] - 1.0) < 1e-6
+
+
+def test_auto_kernel_selection_and_device_entry_point():
+    n, d, nq, k = 10000, 768, 256, 32
+    C, Q = _data(n, d, nq, seed=3)
+    with Index(d, n) as ix:
+        ix.add(C, np.arange(n, dtype=np.int64))
+        ids, sc = ix.search(Q, k)
+        st = ix.stats()
+        assert st["last_kernel"] == N.KERNEL_TC2 and st["last_launches"] >= 2
+        dq = DeviceBuffer(nq * d * 2).upload(to_bf16_bits(Q))
+        ds, di, d64 = DeviceBuffer(nq * k * 4), DeviceBuffer(nq * k * 8), DeviceBuffer(nq * k * 8)
+        ix.search_dev(dq.ptr, nq, k, ds.ptr, di.ptr, d64.ptr)
+        ix.sync()
+        sc_d = ds.download(np.empty((nq, k), np.float32))
+        ids_d = di.download(np.empty((nq, k), np.int64))
+        s64 = d64.download(np.empty((nq, k), np.float64))
+    assert np.array_equal(ids, ids_d) and np.array_equal(sc, sc_d)
+    assert np.array_equal(s64.astype(np.float32), sc_d)
+    assert np.all(np.diff(s64, axis=1) <= 0)                   # sorted best-first
+    _check(ids, sc, *O.cosine_topk(Q, C, k))
+
+
+def test_unsupported_shapes_fail_loudly():
+    with Index(100, 256, dtype="f32") as ix:
+        ix.add(np.ones((4, 100), np.float32), np.arange(4, dtype=np.int64))
+        ix.set_kernel(N.KERNEL_TC2)
+        with pytest.raises(N.AuroraError) as e:
+            ix.search(np.ones((1, 100), np.float32), 2)
+        assert e.value.code == N.AUR_ERR_UNSUPPORTED
+        ix.set_kernel(N.KERNEL_AUTO)
+        with pytest.raises(N.AuroraError):
+            ix.search(np.ones((1, 100), np.float32), 1000)       # k > 128
+    with Index(64, 8) as ix:
+        with pytest.raises(N.AuroraError) as e:
+            ix.add(np.ones((9, 64), np.float32), np.arange(9, dtype=np.int64))
+        assert e.value.code == N.AUR_ERR_NOMEM
+
+
+# ------------------------------------------------------------------ row-sharded corpus: exact cross-shard merge
+def test_two_shards_merge_equals_single_index():
+    n, d, nq, k, G = 40000, 768, 256, 32, 2
+    C, Q = _data(n, d, nq, seed=21)
+    C[100] = C[30000]                                          # a tie across shards
+    full_ids, full_sc = O.cosine_topk(Q, C, k)
+    qbits = to_bf16_bits(Q)
+    per = n // G
+    s64 = np.empty((G, nq, k), np.float64)
+    sid = np.empty((G, nq, k), np.int64)
+    for g in range(G):
+        with Index(d, per) as ix:
+            ix.add(C[g * per:(g + 1) * per], np.arange(g * per, (g + 1) * per, dtype=np.int64))
+            dq = DeviceBuffer(qbits.nbytes).upload(qbits)
+            ds, di, d64 = DeviceBuffer(nq * k * 4), DeviceBuffer(nq * k * 8), DeviceBuffer(nq * k * 8)
+            ix.search_dev(dq.ptr, nq, k, ds.ptr, di.ptr, d64.ptr)
+            ix.sync()
+            s64[g] = d64.download(np.empty((nq, k), np.float64))
+            sid[g] = di.download(np.empty((nq, k), np.int64))
+    din_s, din_i = DeviceBuffer(s64.nbytes).upload(s64), DeviceBuffer(sid.nbytes).upload(sid)
+    dos, doi = DeviceBuffer(nq * k * 4), DeviceBuffer(nq * k * 8)
+    merge_topk_dev(0, din_s.ptr, din_i.ptr, G, nq, k, dos.ptr, doi.ptr)
+    ids = doi.download(np.empty((nq, k), np.int64))
+    sc = dos.download(np.empty((nq, k), np.float32))
+    _check(ids, sc, full_ids, full_sc)
+
+
+# ------------------------------------------------------------------ in-repo cosine (a7)
+def test_cosine_pairs_matches_reference_golden():
+    g = json.load(open(GOLDEN))
+    by_dim = {}
+    for e in g["random_pairs"]:
+        by_dim.setdefault(len(e["a"]), []).append(e)
+    for dim, es in by_dim.items():
+        a = np.array([e["a"] for e in es], dtype=np.float32)
+        b = np.array([e["b"] for e in es], dtype=np.float32)
+        raw = cosine_pairs(a, b)
+        clamped = cosine_pairs(a, b, clamp=True)
+        assert np.allclose(raw, [e["raw"] for e in es], atol=1e-9)
+        assert np.allclose(clamped, [e["clamped"] for e in es], atol=1e-9)
+
+
+# ------------------------------------------------------------------ BASELINE config 2 at full size: properties
+def test_cfg2_full_size_properties():
+    """1M x 768 bf16, 256 queries, top-32: planted neighbours are found in order, the tcgen05
+    variants agree with each other bit for bit, a repeated search is identical, and a
+    subsample of queries matches the oracle."""
+    n, d, nq, k, P = 1_000_000, 768, 256, 32, 8
+    rng = np.random.default_rng(1002)
+    Qf = O.round_to_bf16(np.random.default_rng(2002).standard_normal((nq, d)).astype(np.float32))
+    bits = np.empty((n, d), dtype=np.uint16)
+    for lo in range(0, n, 100_000):
+        bits[lo:lo + 100_000] = to_bf16_bits(rng.standard_normal((100_000, d)).astype(np.float32))
+    prng = np.random.default_rng(3002)
+    planted = prng.choice(n, size=(nq, P), replace=False)
+    for i in range(nq):
+        noise = prng.standard_normal((P, d)).astype(np.float32) * (0.1 * (1 + np.arange(P))[:, None])
+        bits[planted[i]] = to_bf16_bits(Qf[i][None, :] + noise)     # increasing noise => known order
+    with Index(d, n) as ix:
+        for lo in range(0, n, 250_000):
+            ix.add(bits[lo:lo + 250_000], np.arange(lo, lo + 250_000, dtype=np.int64))
+        res = {}
+        for kern in (N.KERNEL_TC2, N.KERNEL_TC1):
+            ix.set_kernel(kern)
+            res[kern] = ix.search(Qf, k)
+        again = ix.search(Qf, k)
+    ids, sc = res[N.KERNEL_TC2]
+    assert np.array_equal(ids[:, :P], planted)                       # planted rows, in noise order
+    assert np.all(np.diff(sc, axis=1) <= 0)
+    assert np.array_equal(res[N.KERNEL_TC1][0], ids) and np.array_equal(res[N.KERNEL_TC1][1], sc)
+    assert np.array_equal(again[0], res[N.KERNEL_TC1][0])
+    sub = [0, 100, 255]
+    oids, osc = O.cosine_topk(Qf[sub], O.bf16_bits_to_f32(bits), k)
+    _check(ids[sub], sc[sub], oids, osc)

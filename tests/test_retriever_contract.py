@@ -1,0 +1,138 @@
+"""Drop-in contract of aurora_b200.retriever vs server/routes/knowledge_base/weaviate_client.py:
+same names, keyword arguments, return shapes and error conventions.  CPU only (the vector
+index is a test double; the GPU-backed run of the same contract is in test_gpu_retriever.py)."""
+
+import inspect
+
+import pytest
+
+from aurora_b200 import retriever as R
+from aurora_b200.filters import Filter, HybridFusion
+from tests.doubles import HashEmbedder, OracleIndex
+
+
+@pytest.fixture()
+def kb():
+    R.configure(encoder=HashEmbedder(64), capacity=4096, index_factory=lambda dim, cap: OracleIndex(dim, cap))
+    yield R
+    R.configure(factory=lambda: (_ for _ in ()).throw(RuntimeError("backend down")))
+
+
+def _chunks(*texts):
+    return [{"content": t, "heading_context": f"Doc > S{i}", "chunk_index": i} for i, t in enumerate(texts)]
+
+
+def test_signatures_match_the_reference_module():
+    # weaviate_client.py:136-142, :215-222, :288, :322, :347, :374
+    sig = lambda f: [(p.name, p.default) for p in inspect.signature(f).parameters.values()]  # noqa: E731
+    E = inspect.Parameter.empty
+    assert sig(R.insert_chunks) == [("user_id", E), ("document_id", E), ("source_filename", E), ("chunks", E), ("org_id", None)]
+    assert sig(R.search_knowledge_base) == [("user_id", E), ("query", E), ("limit", 5), ("alpha", 0.5),
+                                            ("min_score", 0.0), ("org_id", None)]
+    assert sig(R.delete_document_chunks) == [("user_id", E), ("document_id", E)]
+    assert sig(R.delete_user_chunks) == [("user_id", E)]
+    assert sig(R.get_document_chunk_count) == [("user_id", E), ("document_id", E)]
+    assert sig(R.delete_discovery_chunks) == [("org_id", E), ("before", None)]
+    assert R.COLLECTION_NAME == "KnowledgeBaseChunk"
+
+
+def test_insert_search_roundtrip_and_result_shape(kb):
+    n = kb.insert_chunks("u1", "doc-a", "runbook.md",
+                         _chunks("restart the payment service when latency spikes",
+                                 "rotate database credentials every ninety days",
+                                 "kafka consumer lag alert runbook"), org_id="org1")
+    assert n == 3
+    res = kb.search_knowledge_base("u1", "payment service latency", limit=2)
+    assert len(res) == 2
+    assert set(res[0]) == {"content", "heading_context", "source_filename", "document_id", "chunk_index", "score"}  # :269-276
+    assert res[0]["content"].startswith("restart the payment service")
+    assert res[0]["source_filename"] == "runbook.md" and res[0]["document_id"] == "doc-a"
+    assert res[0]["score"] >= res[1]["score"]
+    assert -1.0 <= res[0]["score"] <= 1.0 + 1e-6
+
+
+def test_blank_query_and_empty_chunks(kb):
+    assert kb.search_knowledge_base("u1", "   ") == []        # :237-238
+    assert kb.insert_chunks("u1", "d", "f.md", []) == 0       # :159-160
+
+
+def test_tenant_scope_is_user_or_org(kb):
+    kb.insert_chunks("alice", "d1", "a.md", _chunks("alpha incident postmortem"), org_id="acme")
+    kb.insert_chunks("bob", "d2", "b.md", _chunks("alpha incident postmortem"), org_id="acme")
+    kb.insert_chunks("carol", "d3", "c.md", _chunks("alpha incident postmortem"), org_id="other")
+    own = kb.search_knowledge_base("alice", "alpha incident", limit=10)
+    assert {r["document_id"] for r in own} == {"d1"}                              # no org -> user scope only
+    shared = kb.search_knowledge_base("alice", "alpha incident", limit=10, org_id="acme")
+    assert {r["document_id"] for r in shared} == {"d1", "d2"}                     # :244-249
+    assert kb.search_knowledge_base("nobody", "alpha incident", limit=10) == []
+
+
+def test_min_score_only_filters_when_positive(kb):
+    kb.insert_chunks("u", "d", "f.md", _chunks("cpu saturation on api gateway", "completely unrelated gardening tips"))
+    all_ = kb.search_knowledge_base("u", "api gateway cpu", limit=5, min_score=0.0)
+    assert len(all_) == 2
+    some = kb.search_knowledge_base("u", "api gateway cpu", limit=5, min_score=0.5)   # :266
+    assert [r["content"] for r in some] == ["cpu saturation on api gateway"]
+
+
+def test_upsert_is_idempotent_on_user_doc_chunk(kb):
+    kb.insert_chunks("u", "d", "f.md", _chunks("first version of the text"))
+    kb.insert_chunks("u", "d", "f.md", _chunks("second version of the text"))          # same uuid5 key (:172)
+    assert kb.get_document_chunk_count("u", "d") == 1
+    res = kb.search_knowledge_base("u", "version of the text", limit=5)
+    assert [r["content"] for r in res] == ["second version of the text"]
+
+
+def test_deletes_and_counts(kb):
+    kb.insert_chunks("u", "d1", "f.md", _chunks("one", "two", "three"))
+    kb.insert_chunks("u", "d2", "g.md", _chunks("four"))
+    assert kb.get_document_chunk_count("u", "d1") == 3
+    assert kb.delete_document_chunks("u", "d1") == 3           # :288-319
+    assert kb.get_document_chunk_count("u", "d1") == 0
+    assert kb.delete_document_chunks("u", "d1") == 0
+    assert kb.delete_user_chunks("u") == 1                     # :322-344
+    assert kb.search_knowledge_base("u", "four") == []
+
+
+def test_discovery_chunks_prefix_and_before(kb):
+    kb.insert_chunks("u", "discovery:20260101:aa", "topology", _chunks("service a talks to b"), org_id="o")
+    kb.insert_chunks("u", "manual-doc", "m.md", _chunks("service a talks to b"), org_id="o")
+    assert kb.delete_discovery_chunks("o", before="1999-01-01T00:00:00+00:00") == 0     # created_at < before (:383-384)
+    assert kb.delete_discovery_chunks("o") == 1
+    assert kb.get_document_chunk_count("u", "manual-doc") == 1
+
+
+def test_error_conventions_when_the_backend_is_down():
+    R.configure(factory=lambda: (_ for _ in ()).throw(RuntimeError("backend down")))
+    assert R.search_knowledge_base("u", "q") == []                       # :283-285
+    assert R.delete_document_chunks("u", "d") == -1                      # :317-319
+    assert R.delete_user_chunks("u") == -1                               # :342-344
+    assert R.get_document_chunk_count("u", "d") == 0                     # :369-371
+    assert R.delete_discovery_chunks("o") == 0                           # :392-394
+    with pytest.raises(RuntimeError):                                    # :210-212 re-raises for Celery retry
+        R.insert_chunks("u", "d", "f.md", _chunks("x"))
+
+
+def test_private_client_facade_used_by_rca_prompt_builder(kb):
+    """chat/background/rca_prompt_builder.py:276-317 grabs (client, collection) and runs its own hybrid query."""
+    kb.insert_chunks("u", "discovery:20260101:ab", "gke-topology", _chunks("checkout depends on payments and redis"), org_id="o")
+    kb.insert_chunks("u", "other", "notes.md", _chunks("checkout depends on payments and redis"), org_id="o")
+    client, collection = kb._get_weaviate_client()
+    assert client.is_ready()
+    f = Filter.by_property("org_id").equal("o") & Filter.by_property("document_id").like("discovery:*")
+    resp = collection.query.hybrid(query="checkout payments", limit=3, alpha=0.5, fusion_type=HybridFusion.RANKED,
+                                   filters=f, return_metadata=["score"])
+    assert len(resp.objects) == 1
+    assert resp.objects[0].properties["source_filename"] == "gke-topology"
+    assert resp.objects[0].metadata.score > 0
+
+
+def test_filter_algebra():
+    p = {"org_id": "o", "document_id": "discovery:1", "created_at": "2026-01-01T00:00:00+00:00"}
+    assert Filter.by_property("org_id").equal("o").matches(p)
+    assert not Filter.by_property("org_id").equal("x").matches(p)
+    assert Filter.by_property("document_id").like("discovery:*").matches(p)
+    assert not Filter.by_property("document_id").like("manual*").matches(p)
+    assert Filter.by_property("created_at").less_than("2027").matches(p)
+    assert (Filter.by_property("org_id").equal("x") | Filter.by_property("org_id").equal("o")).matches(p)
+    assert not (Filter.by_property("org_id").equal("x") & Filter.by_property("org_id").equal("o")).matches(p)
