@@ -40,7 +40,7 @@ constexpr int kTcKbPerStage = 4;   // k-blocks per pipeline stage
 constexpr int kTcQRows = 128;      // queries per CTA (TMEM lanes)
 constexpr int kTcChunk = 16;       // scores examined per threshold test
 constexpr int kTcListMin = 64;     // list slots per query: max(ksel, this) so a whole first tile appends
-constexpr int kTcMaxStages = 8;
+constexpr int kTcMaxStages = 12;
 constexpr int kTcMaxDim = 768;     // A operand (queries) must fit 384 TMEM columns
 constexpr int kTcAccCol0 = 384;    // accumulator buffers at TMEM columns 384 / 448
 constexpr int kSlack = 8;          // extra candidates kept for the exact re-rank
@@ -100,6 +100,7 @@ struct FinalizeArgs {
   const void* q; const void* rows; int dtype; int dim; int nq; int k;
   const int64_t* ids;
   float* out_scores; int64_t* out_ids; double* out_scores64;
+  int sort_cap;      // set by launch_finalize: keys the shared sort buffer holds
 };
 cudaError_t launch_finalize(const FinalizeArgs& a, cudaStream_t s);
 cudaError_t launch_merge_topk(const double* in_s, const int64_t* in_ids, int n_shards, int nq, int k,

@@ -3,6 +3,7 @@
 // fp64 re-rank that fixes the final (score desc, id asc) order, the cross-shard merge and
 // the pairwise cosine that mirrors SimilarityStrategy._cosine_similarity.
 #include <math.h>
+#include <string.h>
 #include "internal.h"
 
 namespace aur {
@@ -162,7 +163,7 @@ reduce_lists_kernel(const uint64_t* __restrict__ in, int n_lists, int ksel, int 
 // --------------------------------------------------------------------------------------
 // Finalize: best ksel approximate candidates -> exact fp64 cosine -> (score desc, id asc).
 template <typename T>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(256)
 finalize_kernel(FinalizeArgs a) {
   extern __shared__ uint64_t skeys[];
   __shared__ double ex_score[kMaxK + kSlack];
@@ -172,13 +173,13 @@ finalize_kernel(FinalizeArgs a) {
   const int cap = a.n_lists * a.ksel;                       // row stride of cand
   const int n = a.counts ? min(static_cast<int>(a.counts[qi]), cap) : cap;
   const uint64_t* src = a.cand + static_cast<size_t>(qi) * cap;
-  // Sort in rounds of at most kSortCap keys; the best ksel of earlier rounds ride along
+  // Sort in rounds of at most sort_cap keys; the best ksel of earlier rounds ride along
   // at the front.  (One round unless a compacted row overflows the sort buffer.)
   int P = 1;
   {
     int done = 0, carried = 0;
     do {
-      const int take = min(n - done, kSortCap - carried);
+      const int take = min(n - done, a.sort_cap - carried);
       const int m = carried + take;
       P = 1; while (P < m) P <<= 1;
       for (int i = carried + threadIdx.x; i < P; i += blockDim.x) skeys[i] = (i < m) ? src[done + i - carried] : 0ull;
@@ -191,27 +192,51 @@ finalize_kernel(FinalizeArgs a) {
   __syncthreads();
   if (a.counts && threadIdx.x == 0) a.counts[qi] = 0;      // ready for the next launch
 
+  // Exact re-score.  The query goes to shared memory once (as fp32, exact for bf16 / f32);
+  // a warp takes one candidate: lanes stride over 16-byte pieces of the row, fp64 FMA, fixed
+  // shuffle tree -- a row's score depends only on its content, never on where it is stored.
   const T* rows = static_cast<const T*>(a.rows);
   const T* qv = static_cast<const T*>(a.q) + static_cast<size_t>(qi) * a.dim;
+  float* qs = reinterpret_cast<float*>(skeys + a.sort_cap);      // [dim] behind the sort buffer
+  __shared__ uint64_t topkeys[kMaxK + kSlack];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int ncand = min(a.ksel, P);
+  for (int c = threadIdx.x; c < ncand; c += blockDim.x) topkeys[c] = skeys[c];
+  for (int i = threadIdx.x; i < a.dim; i += blockDim.x) qs[i] = to_f32(qv[i]);
+  __syncthreads();
   if (warp == 0) {
     double qq = 0.0;
-    for (int i = lane; i < a.dim; i += 32) { const double v = static_cast<double>(to_f32(qv[i])); qq = fma(v, v, qq); }
+    for (int i = lane; i < a.dim; i += 32) { const double v = static_cast<double>(qs[i]); qq = fma(v, v, qq); }
     qq = warp_sum_lane0(qq);
     if (lane == 0) s_qq = qq;
   }
   __syncthreads();
-  const int ncand = min(a.ksel, P);
+  constexpr int kVec = 16 / static_cast<int>(sizeof(T));          // elements per 16-byte piece
+  const bool vec_ok = (a.dim % kVec) == 0;
   for (int c = warp; c < ncand; c += nwarps) {
-    const uint64_t key = skeys[c];
+    const uint64_t key = topkeys[c];
     const int32_t row = (key == 0) ? -1 : key_row(key);
     double sc = -INFINITY; int64_t id = -1;
     if (row >= 0) {  // warp-uniform
       const T* rv = rows + static_cast<size_t>(row) * a.dim;
       double dot = 0.0, cc = 0.0;
-      for (int i = lane; i < a.dim; i += 32) {
-        const double x = static_cast<double>(to_f32(qv[i])), y = static_cast<double>(to_f32(rv[i]));
-        dot = fma(x, y, dot); cc = fma(y, y, cc);
+      if (vec_ok) {
+        const uint4* rv4 = reinterpret_cast<const uint4*>(rv);
+        for (int ch = lane; ch < a.dim / kVec; ch += 32) {
+          const uint4 raw = __ldg(rv4 + ch);
+          T el[kVec];
+          memcpy(el, &raw, 16);
+#pragma unroll
+          for (int e = 0; e < kVec; ++e) {
+            const double x = static_cast<double>(qs[ch * kVec + e]), y = static_cast<double>(to_f32(el[e]));
+            dot = fma(x, y, dot); cc = fma(y, y, cc);
+          }
+        }
+      } else {
+        for (int i = lane; i < a.dim; i += 32) {
+          const double x = static_cast<double>(qs[i]), y = static_cast<double>(to_f32(rv[i]));
+          dot = fma(x, y, dot); cc = fma(y, y, cc);
+        }
       }
       dot = warp_sum_lane0(dot); cc = warp_sum_lane0(cc);
       const double den = sqrt(s_qq) * sqrt(cc);
@@ -358,15 +383,23 @@ cudaError_t launch_reduce_lists(const uint64_t* in, int nq, int n_lists, int kse
   return cudaGetLastError();
 }
 
-cudaError_t launch_finalize(const FinalizeArgs& a, cudaStream_t s) {
+cudaError_t launch_finalize(const FinalizeArgs& a_in, cudaStream_t s) {
+  FinalizeArgs a = a_in;
   int P = 1; while (P < a.n_lists * a.ksel) P <<= 1;
   if (P > kSortCap) {
     if (!a.counts) return cudaErrorInvalidValue;   // dense rows must be folded first
     P = kSortCap;
   }
-  const size_t smem = static_cast<size_t>(P) * 8;
-  if (a.dtype == 0) finalize_kernel<__nv_bfloat16><<<a.nq, 512, smem, s>>>(a);
-  else finalize_kernel<float><<<a.nq, 512, smem, s>>>(a);
+  a.sort_cap = P;
+  const size_t smem = static_cast<size_t>(P) * 8 + static_cast<size_t>(a.dim) * 4;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(a.dtype == 0 ? (const void*)finalize_kernel<__nv_bfloat16>
+                                                      : (const void*)finalize_kernel<float>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+  }
+  if (a.dtype == 0) finalize_kernel<__nv_bfloat16><<<a.nq, 256, smem, s>>>(a);
+  else finalize_kernel<float><<<a.nq, 256, smem, s>>>(a);
   return cudaGetLastError();
 }
 

@@ -177,7 +177,9 @@ def run_ours(args):
     row_lo = rank * per
     n_local = per if rank < world - 1 else N_ROWS - row_lo
     ix = Index(DIM, n_local, dtype="bf16", device=local)
-    stream = torch.cuda.current_stream().cuda_stream
+    # the C ABI reads NULL as "the index's own stream"; torch's default stream is the legacy
+    # stream, whose explicit handle is cudaStreamLegacy (0x1)
+    stream = torch.cuda.current_stream().cuda_stream or 1
     chunk = 125_000
     for lo in range(0, n_local, chunk):
         m = min(chunk, n_local - lo)

@@ -14,7 +14,8 @@
  *     buffer has been written and aur_last_error() (thread-local) describes why;
  *   - "host" entry points take host pointers and include the H2D / D2H copies;
  *     "_dev" entry points take device pointers on the index's device and a cudaStream_t
- *     passed as void* (NULL = the index's own stream) and do not synchronise;
+ *     passed as void* (NULL = the index's own stream; pass cudaStreamLegacy, (void*)1, for
+ *     the legacy default stream) and do not synchronise;
  *   - vectors are row-major [n, dim]; dtype is fixed per index (AUR_BF16: raw uint16
  *     bfloat16 bits; AUR_F32: IEEE float);
  *   - ids are caller-chosen int64 (>= 0), unique per index; adding an existing id
