@@ -138,9 +138,9 @@ int run_tc_block(aur_index* ix, int cta_group, const void* q_dev, int nqb, int k
   if (cta_group == 2 && n_qblocks != 2) cta_group = 1;  // a pair needs 256 query rows
   int grid = ix->sm_count & ~1;
   const int n_tsets = (cta_group == 2) ? grid / 2 : grid / n_qblocks;
-  // two epilogue groups (alternating tiles) whenever their lists leave room for >= 4 pipeline stages
+  // epilogue groups: 1 by default; 2 (alternating tiles) stays selectable for experiments
   int epi_groups = ix->opt_epi_groups;
-  if (epi_groups == 0) epi_groups = tc_pick_stages(cta_group, 2, ksel, ix->smem_optin) >= 4 ? 2 : 1;
+  if (epi_groups == 0) epi_groups = 1;   // measured: one group + a deeper TMA ring (11 stages) beats two groups + 8
   const int stages = tc_pick_stages(cta_group, epi_groups, ksel, ix->smem_optin);
   if (stages < 2) return fail(AUR_ERR_UNSUPPORTED, "k too large for the tcgen05 path's shared memory");
   const size_t smem = tc_smem_bytes(cta_group, epi_groups, stages, ksel);
