@@ -163,7 +163,7 @@ reduce_lists_kernel(const uint64_t* __restrict__ in, int n_lists, int ksel, int 
 // --------------------------------------------------------------------------------------
 // Finalize: best ksel approximate candidates -> exact fp64 cosine -> (score desc, id asc).
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 finalize_kernel(FinalizeArgs a) {
   extern __shared__ uint64_t skeys[];
   __shared__ double ex_score[kMaxK + kSlack];
@@ -213,37 +213,54 @@ finalize_kernel(FinalizeArgs a) {
   __syncthreads();
   constexpr int kVec = 16 / static_cast<int>(sizeof(T));          // elements per 16-byte piece
   const bool vec_ok = (a.dim % kVec) == 0;
-  for (int c = warp; c < ncand; c += nwarps) {
-    const uint64_t key = topkeys[c];
-    const int32_t row = (key == 0) ? -1 : key_row(key);
-    double sc = -INFINITY; int64_t id = -1;
-    if (row >= 0) {  // warp-uniform
-      const T* rv = rows + static_cast<size_t>(row) * a.dim;
-      double dot = 0.0, cc = 0.0;
-      if (vec_ok) {
-        const uint4* rv4 = reinterpret_cast<const uint4*>(rv);
-        for (int ch = lane; ch < a.dim / kVec; ch += 32) {
-          const uint4 raw = __ldg(rv4 + ch);
+  // two candidates per warp and step: both rows' loads are in flight before any arithmetic
+  for (int c0 = 2 * warp; c0 < ncand; c0 += 2 * nwarps) {
+    int32_t row[2]; const T* rv[2];
+    double dot[2] = {0.0, 0.0}, cc[2] = {0.0, 0.0};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint64_t key = (c0 + h < ncand) ? topkeys[c0 + h] : 0ull;
+      row[h] = (key == 0) ? -1 : key_row(key);
+      rv[h] = rows + static_cast<size_t>(row[h] < 0 ? 0 : row[h]) * a.dim;
+    }
+    if (vec_ok) {
+      for (int ch = lane; ch < a.dim / kVec; ch += 32) {
+        uint4 raw[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) raw[h] = (row[h] >= 0) ? __ldg(reinterpret_cast<const uint4*>(rv[h]) + ch) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
           T el[kVec];
-          memcpy(el, &raw, 16);
+          memcpy(el, &raw[h], 16);
 #pragma unroll
           for (int e = 0; e < kVec; ++e) {
             const double x = static_cast<double>(qs[ch * kVec + e]), y = static_cast<double>(to_f32(el[e]));
-            dot = fma(x, y, dot); cc = fma(y, y, cc);
+            dot[h] = fma(x, y, dot[h]); cc[h] = fma(y, y, cc[h]);
           }
         }
-      } else {
-        for (int i = lane; i < a.dim; i += 32) {
-          const double x = static_cast<double>(qs[i]), y = static_cast<double>(to_f32(rv[i]));
-          dot = fma(x, y, dot); cc = fma(y, y, cc);
+      }
+    } else {
+      for (int i = lane; i < a.dim; i += 32) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (row[h] < 0) continue;
+          const double x = static_cast<double>(qs[i]), y = static_cast<double>(to_f32(rv[h][i]));
+          dot[h] = fma(x, y, dot[h]); cc[h] = fma(y, y, cc[h]);
         }
       }
-      dot = warp_sum_lane0(dot); cc = warp_sum_lane0(cc);
-      const double den = sqrt(s_qq) * sqrt(cc);
-      sc = den > 0.0 ? dot / den : 0.0;  // zero norm -> 0.0 (similarity.py:94-95)
-      id = a.ids[row];
     }
-    if (lane == 0) { ex_score[c] = sc; ex_id[c] = id; }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (c0 + h >= ncand) break;
+      double sc = -INFINITY; int64_t id = -1;
+      if (row[h] >= 0) {   // warp-uniform
+        const double d = warp_sum_lane0(dot[h]), n2 = warp_sum_lane0(cc[h]);
+        const double den = sqrt(s_qq) * sqrt(n2);
+        sc = den > 0.0 ? d / den : 0.0;  // zero norm -> 0.0 (similarity.py:94-95)
+        id = a.ids[row[h]];
+      }
+      if (lane == 0) { ex_score[c0 + h] = sc; ex_id[c0 + h] = id; }
+    }
   }
   __syncthreads();
   // rank by counting: ids are unique, so (score desc, id asc) is a total order
@@ -398,8 +415,8 @@ cudaError_t launch_finalize(const FinalizeArgs& a_in, cudaStream_t s) {
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
   }
-  if (a.dtype == 0) finalize_kernel<__nv_bfloat16><<<a.nq, 256, smem, s>>>(a);
-  else finalize_kernel<float><<<a.nq, 256, smem, s>>>(a);
+  if (a.dtype == 0) finalize_kernel<__nv_bfloat16><<<a.nq, 512, smem, s>>>(a);
+  else finalize_kernel<float><<<a.nq, 512, smem, s>>>(a);
   return cudaGetLastError();
 }
 
