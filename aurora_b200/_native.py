@@ -24,6 +24,8 @@ EXPORTS = [
     "aur_set_option", "aur_sync", "aur_add", "aur_add_dev", "aur_remove", "aur_search", "aur_search_dev",
     "aur_merge_topk_dev", "aur_cosine_pairs", "aur_dev_malloc", "aur_dev_free", "aur_memcpy_h2d", "aur_memcpy_d2h",
     "aur_debug_tc_scores",
+    "aur_encoder_open", "aur_encoder_close", "aur_encoder_load", "aur_encode", "aur_encode_append",
+    "aur_encoder_get_stats", "aur_debug_gemm", "aur_debug_attention", "aur_debug_encoder_hidden",
 ]
 
 
@@ -36,6 +38,18 @@ class AurStats(C.Structure):
     _fields_ = [("rows", C.c_int64), ("live", C.c_int64), ("capacity", C.c_int64), ("dim", C.c_int32),
                 ("dtype", C.c_int32), ("last_kernel", C.c_int32), ("last_launches", C.c_int32),
                 ("last_kernel_ms", C.c_float), ("last_total_ms", C.c_float)]
+
+
+class AurEncoderConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("hidden", C.c_int32), ("layers", C.c_int32), ("heads", C.c_int32),
+                ("inter", C.c_int32), ("vocab", C.c_int32), ("max_pos", C.c_int32), ("type_vocab", C.c_int32),
+                ("pool", C.c_int32), ("normalize", C.c_int32), ("max_tokens", C.c_int32), ("max_seqs", C.c_int32),
+                ("ln_eps", C.c_float), ("reserved", C.c_int32)]
+
+
+class AurEncoderStats(C.Structure):
+    _fields_ = [("tokens", C.c_int64), ("seqs", C.c_int64), ("launches", C.c_int32), ("total_ms", C.c_float),
+                ("gemm_ms", C.c_float), ("attn_ms", C.c_float), ("gemm_flops", C.c_double), ("attn_flops", C.c_double)]
 
 
 class NativeLibraryMissing(RuntimeError):
@@ -83,6 +97,15 @@ def load():
         "aur_memcpy_h2d": (C.c_int, [i32, vp, vp, C.c_uint64]),
         "aur_memcpy_d2h": (C.c_int, [i32, vp, vp, C.c_uint64]),
         "aur_debug_tc_scores": (C.c_int, [vp, vp, i32, i32, vp, C.POINTER(i32), vp]),
+        "aur_encoder_open": (C.c_int, [C.POINTER(AurEncoderConfig), C.POINTER(vp)]),
+        "aur_encoder_close": (C.c_int, [vp]),
+        "aur_encoder_load": (C.c_int, [vp, C.c_char_p, vp, i64]),
+        "aur_encode": (C.c_int, [vp, vp, vp, i32, vp, vp]),
+        "aur_encode_append": (C.c_int, [vp, vp, vp, vp, i32, vp, vp, vp]),
+        "aur_encoder_get_stats": (C.c_int, [vp, C.POINTER(AurEncoderStats)]),
+        "aur_debug_gemm": (C.c_int, [i32, vp, vp, vp, vp, i32, i32, i32, i32, vp, C.POINTER(C.c_float)]),
+        "aur_debug_attention": (C.c_int, [i32, vp, vp, i32, i32, i32, vp, C.POINTER(C.c_float)]),
+        "aur_debug_encoder_hidden": (C.c_int, [vp, vp, i64]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

@@ -71,6 +71,28 @@ struct DevBuf {  // grow-only device scratch
 
 }  // namespace
 
+namespace aur {
+int report_error(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  g_err = buf;
+  return code;
+}
+int encode_tmap_2d_bf16(void* tmap, const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
+                        uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return -1;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return static_cast<int>(enc(static_cast<CUtensorMap*>(tmap), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                              const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
+}
+}  // namespace aur
+
 struct aur_index {
   std::mutex mu;
   int device = 0, dim = 0, dtype = 0;

@@ -1,0 +1,227 @@
+// Encoder GEMM on tcgen05:  out[M, N] = act( A[M, K] . W[N, K]^T + bias ) (+ residual), bf16 in,
+// fp32 accumulate in TMEM, bf16 out.  Both operands are K-major (activations [tokens, K] and
+// torch-Linear weights [N, K]), so one {64 x rows} SWIZZLE_128B TMA box feeds either side.
+//
+// Persistent kernel, one CTA per SM, 128 x BN output tiles handed out round-robin:
+//   warp 0      TMA producer   (A 16 KB + W BN*128 B per 64-wide k-block, kStages ring)
+//   warp 1      MMA issuer     (4 x tcgen05.mma M128 N=BN K16 per k-block; two TMEM accumulators
+//                               so the epilogue of tile i overlaps the MMAs of tile i+1)
+//   warps 2..9  epilogue       (thread = output row; two warps per TMEM lane quarter split the
+//                               BN columns; bias / GELU / residual fused, 64-byte row stores)
+// SURVEY.md section 8 a11 (BERT-family encoder forward); structural oracle: oracle/bert_encoder.py.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace aur {
+namespace {
+
+using namespace ptx;
+
+constexpr int kBM = 128, kBK = 64, kEpiWarps = 8, kGemmThreads = (2 + kEpiWarps) * 32;
+
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+
+// GELU, exact-erf form (HF "gelu").  erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, far below the
+// bf16 rounding of the result); one MUFU.RCP + one MUFU.EX2 per element.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = exp2f(-z * z * 1.4426950408889634f);
+  const float erf_abs = fmaf(-poly * t, e, 1.0f);
+  const float erf_x = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erf_x);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kABytes = kBM * kBK * 2;          // 16 KB
+  static constexpr int kBBytes = BN * kBK * 2;           // 16 / 32 KB
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kBarBytes = 256;
+  static constexpr size_t kTotal = 1024 + static_cast<size_t>(kStages) * kStageBytes + kBarBytes;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const GemmParams p) {
+  using S = GemmSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (base & 1023u)) & 1023u);
+  uint8_t* stage0 = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
+  uint64_t* full = bars;                       // [kStages]
+  uint64_t* empty = bars + S::kStages;         // [kStages]
+  uint64_t* acc_full = bars + 2 * S::kStages;  // [2]
+  uint64_t* acc_empty = acc_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles_total = p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
+    for (int s = 0; s < S::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], kEpiWarps); }
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc<1>(tmem_slot, 2 * BN); tmem_relinquish<1>(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+      const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          uint8_t* sa = stage0 + stage * S::kStageBytes;
+          mbar_arrive_expect_tx(&full[stage], S::kStageBytes);
+          tma_load_2d(sa, &tmap_a, &full[stage], kb * kBK, m_blk * kBM, kEvictNormal);
+          tma_load_2d(sa + S::kABytes, &tmap_b, &full[stage], kb * kBK, n_blk * BN, kEvictLast);
+        }
+        __syncwarp();
+        if (++stage == S::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = idesc_bf16_f32(kBM, BN);
+    int stage = 0; uint32_t phase = 0; int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(stage0 + stage * S::kStageBytes);
+        const uint64_t a_desc = smem_desc_sw128(sa), b_desc = smem_desc_sw128(sa + S::kABytes);
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < kBK / 16; ++ks)
+            mma_ss_bf16<1>(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kb | ks) != 0);
+          mma_commit<1>(&empty[stage]);
+          if (kb == p.k_blocks - 1) mma_commit<1>(&acc_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == S::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue
+    const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
+    constexpr int kColsPerWarp = BN / 2;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
+      const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
+      const int acc = it & 1;
+      mbar_wait(&acc_full[acc], (it >> 1) & 1);
+      tc_fence_after();
+      const int row = m_blk * kBM + quarter * 32 + lane;
+      const int col0 = n_blk * BN + half * kColsPerWarp;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * kColsPerWarp;
+      __nv_bfloat16* orow = p.out + static_cast<size_t>(row) * p.ldo + col0;
+      const __nv_bfloat16* rrow = EPI == kEpiBiasResid ? p.resid + static_cast<size_t>(row) * p.ldr + col0 : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < kColsPerWarp; c += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(taddr + c, v);
+        uint4 res[4];
+        if constexpr (EPI == kEpiBiasResid) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) res[j] = __ldg(reinterpret_cast<const uint4*>(rrow + c) + j);
+        }
+        tmem_wait_ld();
+        uint32_t o[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c) + j);
+          float x0 = __uint_as_float(v[4 * j + 0]) + b.x, x1 = __uint_as_float(v[4 * j + 1]) + b.y;
+          float x2 = __uint_as_float(v[4 * j + 2]) + b.z, x3 = __uint_as_float(v[4 * j + 3]) + b.w;
+          if constexpr (EPI == kEpiBiasGelu) { x0 = gelu_erf(x0); x1 = gelu_erf(x1); x2 = gelu_erf(x2); x3 = gelu_erf(x3); }
+          if constexpr (EPI == kEpiBiasResid) {
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(res);
+            x0 += bf16_lo(rw[2 * j]); x1 += bf16_hi(rw[2 * j]); x2 += bf16_lo(rw[2 * j + 1]); x3 += bf16_hi(rw[2 * j + 1]);
+          }
+          o[2 * j] = pack_bf16x2(x0, x1); o[2 * j + 1] = pack_bf16x2(x2, x3);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          reinterpret_cast<uint4*>(orow + c)[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc<1>(tmem_base, 2 * BN); }
+}
+
+template <int BN, int EPI>
+cudaError_t launch_one(int grid, const void* tmap_a, const void* tmap_b, const GemmParams& p, cudaStream_t s) {
+  auto kern = gemm_tc_kernel<BN, EPI>;
+  static bool attr_set = false;   // per instantiation; cudaFuncSetAttribute is idempotent
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(GemmSmem<BN>::kTotal));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  kern<<<grid, kGemmThreads, GemmSmem<BN>::kTotal, s>>>(*reinterpret_cast<const CUtensorMap*>(tmap_a),
+                                                       *reinterpret_cast<const CUtensorMap*>(tmap_b), p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t gemm_tc_launch(int bn, int epi, int sm_count, const void* tmap_a, const void* tmap_b, const GemmParams& p,
+                           cudaStream_t s) {
+  const int tiles = p.m_tiles * p.n_tiles;
+  if (tiles <= 0) return cudaSuccess;
+  const int grid = tiles < sm_count ? tiles : sm_count;
+#define AUR_GEMM_CASE(BN, EPI) \
+  if (bn == BN && epi == EPI) return launch_one<BN, EPI>(grid, tmap_a, tmap_b, p, s)
+  AUR_GEMM_CASE(256, kEpiBias); AUR_GEMM_CASE(256, kEpiBiasGelu); AUR_GEMM_CASE(256, kEpiBiasResid);
+  AUR_GEMM_CASE(128, kEpiBias); AUR_GEMM_CASE(128, kEpiBiasGelu); AUR_GEMM_CASE(128, kEpiBiasResid);
+#undef AUR_GEMM_CASE
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace aur

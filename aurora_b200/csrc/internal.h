@@ -109,4 +109,44 @@ cudaError_t launch_cosine_pairs(const float* a, const float* b, int64_t n, int d
                                 cudaStream_t s);
 cudaError_t launch_fill_f32(float* p, float v, int64_t n, cudaStream_t s);
 
+// ---------------------------------------------------------------- encoder (BERT-family forward)
+// out = epi(A . W^T + bias): A [m_tiles*128, K] bf16 (TMA box {64,128}), W [N, K] bf16 (TMA box {64,BN}).
+enum { kEpiBias = 0, kEpiBiasGelu = 1, kEpiBiasResid = 2 };
+struct GemmParams {
+  const float* bias;            // [N]
+  const __nv_bfloat16* resid;   // [rows, ldr] (kEpiBiasResid only)
+  __nv_bfloat16* out;           // [rows, ldo]
+  int ldo, ldr;
+  int m_tiles, n_tiles, k_blocks;   // 128-row tiles, BN-column tiles, 64-wide k-blocks
+};
+cudaError_t gemm_tc_launch(int bn, int epi, int sm_count, const void* tmap_a, const void* tmap_b, const GemmParams& p,
+                           cudaStream_t s);
+
+// Self-attention over packed variable-length sequences (<= 512 tokens each), head dim 64.
+// One work item = (sequence, 128-query block); every item runs for all heads.
+struct AttnItem { int32_t tok0, len, q0, pad; };   // first token row, length, first query of the block
+struct AttnParams {
+  const AttnItem* items; int n_items; int heads; int hidden;
+  __nv_bfloat16* ctx; int ld_ctx;     // [tokens, hidden] context output
+  float scale_log2e;                  // log2(e) / sqrt(head_dim)
+};
+// tmap_qkv: CUtensorMap over the packed [tokens, 3*hidden] projections, box {64, 128}, SWIZZLE_128B.
+cudaError_t attn_tc_launch(int sm_count, const void* tmap_qkv, const AttnParams& p, cudaStream_t s);
+
+cudaError_t launch_embed_ln(const int32_t* tok, const int32_t* pos, int n_tok, int n_rows_pad,
+                            const __nv_bfloat16* word, const __nv_bfloat16* pos_emb, const __nv_bfloat16* type_emb,
+                            const float* g, const float* b, float eps, int hidden, __nv_bfloat16* out, cudaStream_t s);
+cudaError_t launch_layernorm(const __nv_bfloat16* in, const float* g, const float* b, float eps, int n_rows, int hidden,
+                             __nv_bfloat16* out, cudaStream_t s);
+// pool_mode 0 = first token (CLS), 1 = mean over the sequence; optional L2 normalisation.
+cudaError_t launch_pool(const __nv_bfloat16* x, const int32_t* cu, int n_seq, int hidden, int pool_mode, int normalize,
+                        float* out_f32, __nv_bfloat16* out_bf16, cudaStream_t s);
+cudaError_t launch_f32_to_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s);
+
+// Error reporting shared by the translation units behind the C ABI (thread-local message).
+int report_error(int code, const char* fmt, ...);
+// 2-D bf16 tensor map, 128-byte swizzle; returns 0 or a CUresult.
+int encode_tmap_2d_bf16(void* tmap, const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
+                        uint32_t box_cols, uint32_t box_rows);
+
 }  // namespace aur

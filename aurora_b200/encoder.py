@@ -1,0 +1,204 @@
+"""Python handle over the CUDA text encoder (C ABI: aur_encoder_* in include/aurora_b200.h) and
+the host-side mirror of the reference's embedding client.
+
+Reference surface mirrored here: ``EmbeddingClient.embed / embed_batch / close`` and
+``get_embedding_client()`` (server/services/correlation/embedding_client.py:20-84): ``None`` for
+blank text or any failure, a list of floats otherwise.  The reference posts the text to a
+t2v-transformers sidecar; here the forward pass runs in-process on the GPU.  Tokenisation is the
+caller's (a ``tokenize(text) -> list[int]`` callable): a WordPiece tokenizer needs a vocabulary
+file, which is deployment data, not code.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import logging
+from dataclasses import dataclass
+from functools import lru_cache
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+
+logger = logging.getLogger(__name__)
+
+POOL = {"cls": 0, "mean": 1}
+
+
+@dataclass(frozen=True)
+class EncoderConfig:
+    hidden: int = 768
+    layers: int = 12
+    heads: int = 12
+    inter: int = 3072
+    vocab: int = 30522
+    max_pos: int = 512
+    type_vocab: int = 2
+    ln_eps: float = 1e-12
+    pool: str = "cls"
+    normalize: bool = True
+
+
+BGE_BASE = EncoderConfig()
+MINILM_L6 = EncoderConfig(hidden=384, layers=6, heads=12, inter=1536, pool="mean")   # head dim 32: not yet served by attn_tc.cu
+BGE_LARGE = EncoderConfig(hidden=1024, layers=24, heads=16, inter=4096)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def pack_sequences(seqs: Sequence[Sequence[int]]):
+    """list of token-id lists -> (tokens int32 [total], cu_seqlens int32 [n+1])."""
+    lens = np.fromiter((len(s) for s in seqs), dtype=np.int64, count=len(seqs))
+    cu = np.zeros(len(seqs) + 1, dtype=np.int32)
+    cu[1:] = np.cumsum(lens)
+    tok = np.empty(int(cu[-1]), dtype=np.int32)
+    for i, s in enumerate(seqs):
+        tok[cu[i]:cu[i + 1]] = s
+    return tok, cu
+
+
+class Encoder:
+    """BERT-family encoder resident on one GPU: packed token ids in, pooled vectors out."""
+
+    def __init__(self, cfg: EncoderConfig, max_tokens: int = 32768, max_seqs: int = 2048, device: int = 0):
+        self._lib = N.load()
+        self.cfg, self.device = cfg, int(device)
+        self.max_tokens, self.max_seqs = int(max_tokens), int(max_seqs)
+        self._h = C.c_void_p()
+        c = N.AurEncoderConfig(device=self.device, hidden=cfg.hidden, layers=cfg.layers, heads=cfg.heads, inter=cfg.inter,
+                               vocab=cfg.vocab, max_pos=cfg.max_pos, type_vocab=cfg.type_vocab, pool=POOL[cfg.pool],
+                               normalize=int(cfg.normalize), max_tokens=self.max_tokens, max_seqs=self.max_seqs,
+                               ln_eps=cfg.ln_eps, reserved=0)
+        N.check(self._lib.aur_encoder_open(C.byref(c), C.byref(self._h)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.aur_encoder_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -------------------------------------------------------------- parameters
+    def load_weights(self, weights: Dict[str, np.ndarray]) -> None:
+        """Names and shapes as documented at aur_encoder_load (torch.nn.Linear layout)."""
+        for name, w in weights.items():
+            a = np.ascontiguousarray(w, dtype=np.float32)
+            N.check(self._lib.aur_encoder_load(self._h, name.encode(), _ptr(a), a.size))
+
+    # -------------------------------------------------------------- forward
+    def _check_batch(self, tokens, cu):
+        tokens = np.ascontiguousarray(tokens, dtype=np.int32)
+        cu = np.ascontiguousarray(cu, dtype=np.int32)
+        if cu.ndim != 1 or cu.size < 2 or tokens.ndim != 1 or tokens.size != int(cu[-1]):
+            raise ValueError("tokens [total] and cu_seqlens [n_seq + 1] with cu[-1] == total are required")
+        return tokens, cu
+
+    def encode_packed(self, tokens: np.ndarray, cu_seqlens: np.ndarray, bf16: bool = False) -> np.ndarray:
+        """[n_seq, hidden] float32 (or raw bf16 bits as uint16 when ``bf16``)."""
+        tokens, cu = self._check_batch(tokens, cu_seqlens)
+        n = cu.size - 1
+        out = np.empty((n, self.cfg.hidden), dtype=np.uint16 if bf16 else np.float32)
+        N.check(self._lib.aur_encode(self._h, _ptr(tokens), _ptr(cu), n, None if bf16 else _ptr(out),
+                                     _ptr(out) if bf16 else None))
+        return out
+
+    def encode(self, seqs: Sequence[Sequence[int]]) -> np.ndarray:
+        """Token-id lists of any count: split into calls that fit the workspace."""
+        out = np.empty((len(seqs), self.cfg.hidden), dtype=np.float32)
+        i = 0
+        while i < len(seqs):
+            j, toks = i, 0
+            while j < len(seqs) and j - i < self.max_seqs and toks + len(seqs[j]) <= self.max_tokens:
+                toks += len(seqs[j]); j += 1
+            if j == i:
+                raise ValueError(f"sequence {i} has {len(seqs[i])} tokens: more than max_tokens={self.max_tokens}")
+            tok, cu = pack_sequences(seqs[i:j])
+            out[i:j] = self.encode_packed(tok, cu)
+            i = j
+        return out
+
+    def encode_append(self, index, tokens: np.ndarray, cu_seqlens: np.ndarray, ids: np.ndarray,
+                      user_codes: Optional[np.ndarray] = None, org_codes: Optional[np.ndarray] = None) -> None:
+        """Fused ingest: encode and append to ``index`` (engine.Index) without leaving the device."""
+        tokens, cu = self._check_batch(tokens, cu_seqlens)
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        u = None if user_codes is None else np.ascontiguousarray(user_codes, dtype=np.int32)
+        o = None if org_codes is None else np.ascontiguousarray(org_codes, dtype=np.int32)
+        N.check(self._lib.aur_encode_append(self._h, index._h, _ptr(tokens), _ptr(cu), cu.size - 1, _ptr(ids), _ptr(u), _ptr(o)))
+
+    def stats(self) -> dict:
+        st = N.AurEncoderStats()
+        N.check(self._lib.aur_encoder_get_stats(self._h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in st._fields_}
+
+    def hidden_states(self) -> np.ndarray:
+        """Final hidden states [tokens, hidden] (bf16 bits) of the last call (test hook)."""
+        t = self.stats()["tokens"]
+        out = np.empty((t, self.cfg.hidden), dtype=np.uint16)
+        N.check(self._lib.aur_debug_encoder_hidden(self._h, _ptr(out), out.size))
+        return out
+
+
+# ----------------------------------------------------------------------------- reference mirror
+class EmbeddingClient:
+    """Drop-in for server/services/correlation/embedding_client.py:20-78 backed by ``Encoder``."""
+
+    def __init__(self, encoder: Encoder, tokenize: Callable[[str], List[int]]):
+        self._enc, self._tok = encoder, tokenize
+
+    def embed(self, text: str) -> Optional[List[float]]:
+        if not text or not text.strip():                      # embedding_client.py:48-49
+            return None
+        try:
+            return self._enc.encode([self._tok(text)])[0].tolist()
+        except Exception as e:                                  # embedding_client.py:66-70: any failure -> None
+            logger.warning("[EmbeddingClient] embed failed: %s", e)
+            return None
+
+    def embed_batch(self, texts: List[str]) -> List[Optional[List[float]]]:
+        """One batched forward instead of the reference's per-text loop (embedding_client.py:72-74);
+        blank texts and failures still map to None per element."""
+        idx = [i for i, t in enumerate(texts) if t and t.strip()]
+        out: List[Optional[List[float]]] = [None] * len(texts)
+        if not idx:
+            return out
+        try:
+            vecs = self._enc.encode([self._tok(texts[i]) for i in idx])
+            for j, i in enumerate(idx):
+                out[i] = vecs[j].tolist()
+        except Exception as e:
+            logger.warning("[EmbeddingClient] embed_batch failed: %s", e)
+        return out
+
+    def close(self) -> None:                                    # embedding_client.py:76-78
+        self._enc.close()
+
+
+_factory: Optional[Callable[[], EmbeddingClient]] = None
+
+
+def configure_embedding_client(factory: Callable[[], EmbeddingClient]) -> None:
+    """Deployment hook: how to build the process-wide client (weights, tokenizer, device)."""
+    global _factory
+    _factory = factory
+    get_embedding_client.cache_clear()
+
+
+@lru_cache(maxsize=1)
+def get_embedding_client() -> EmbeddingClient:                 # embedding_client.py:81-84
+    if _factory is None:
+        raise RuntimeError("call aurora_b200.encoder.configure_embedding_client(factory) first")
+    return _factory()

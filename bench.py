@@ -225,9 +225,10 @@ def run_ours(args):
         e1.record()
         barrier()
         # keep the sampler running a little so short runs still get a few samples under load
+        # (local search only: a time-bounded loop must not contain collectives)
         t_end = time.time() + 1.0
         while time.time() < t_end:
-            step_dev()
+            ix.search_dev(q_dev.data_ptr(), NQ, TOPK, sc.data_ptr(), ids.data_ptr(), s64.data_ptr(), stream=stream)
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     if world > 1:

@@ -144,7 +144,71 @@ int aur_dev_free(int32_t device, void* p);
 int aur_memcpy_h2d(int32_t device, void* dst_dev, const void* src_host, uint64_t bytes);
 int aur_memcpy_d2h(int32_t device, void* dst_host, const void* src_dev, uint64_t bytes);
 
+/* ------------------------------------------------------------------ text encoder
+ * Replaces the text2vec-transformers sidecar: EmbeddingClient.embed / embed_batch
+ * (server/services/correlation/embedding_client.py:39-78, POST {base}/vectors) and the
+ * server-side vectorisation Weaviate performs on insert and on hybrid / near_text queries
+ * (server/routes/knowledge_base/weaviate_client.py:113-126, :252-259).  A BERT-family encoder
+ * forward (embeddings, L x [QKV GEMM, attention, out-proj + LayerNorm, FFN + LayerNorm],
+ * pooling) in bf16 with fp32 accumulation.  Input is WordPiece token ids, packed:
+ * tokens [total] and cu_seqlens [n_seq + 1] (sequence i = tokens[cu[i] : cu[i+1]], each
+ * 1..max_pos long, [CLS] / [SEP] included by the caller). */
+typedef struct aur_encoder aur_encoder;
+
+typedef enum aur_pool { AUR_POOL_CLS = 0, AUR_POOL_MEAN = 1 } aur_pool;
+
+typedef struct aur_encoder_config {
+  int32_t device;
+  int32_t hidden, layers, heads, inter;   /* head dim (hidden / heads) must be 64         */
+  int32_t vocab, max_pos, type_vocab;     /* max_pos <= 512                               */
+  int32_t pool;                           /* aur_pool                                     */
+  int32_t normalize;                      /* != 0: L2-normalise the pooled vector         */
+  int32_t max_tokens;                     /* packed tokens per aur_encode call (workspace)*/
+  int32_t max_seqs;                       /* sequences per call                           */
+  float   ln_eps;
+  int32_t reserved;
+} aur_encoder_config;
+
+typedef struct aur_encoder_stats {
+  int64_t tokens, seqs;      /* of the last call                                          */
+  int32_t launches;          /* kernels launched by the last call                         */
+  float   total_ms;          /* device time of the last forward (embeddings .. pooling)   */
+  float   gemm_ms, attn_ms;  /* thereof: tcgen05 GEMMs, attention                          */
+  double  gemm_flops;        /* 2*M*N*K summed over the GEMMs, M = real (unpadded) tokens  */
+  double  attn_flops;        /* 4 * len^2 * hidden per sequence and layer                  */
+} aur_encoder_stats;
+
+int aur_encoder_open(const aur_encoder_config* cfg, aur_encoder** out);
+int aur_encoder_close(aur_encoder* enc);
+/* Upload one parameter tensor (host fp32; matrices are stored as bf16 on the device).  Names:
+ * word_emb [vocab,H], pos_emb [max_pos,H], type_emb [type_vocab,H], emb_ln_g/emb_ln_b [H], and per
+ * layer l: l{l}.wqkv [3H,H] (query, key, value rows stacked), l{l}.bqkv [3H], l{l}.wo [H,H],
+ * l{l}.bo, l{l}.ln1_g, l{l}.ln1_b, l{l}.wi [I,H], l{l}.bi [I], l{l}.wo2 [H,I], l{l}.bo2,
+ * l{l}.ln2_g, l{l}.ln2_b -- all [out_features, in_features] like torch.nn.Linear. */
+int aur_encoder_load(aur_encoder* enc, const char* name, const float* data, int64_t count);
+/* Host in / host out.  out_f32 [n_seq, hidden] and/or out_bf16 [n_seq, hidden] (either may be
+ * NULL).  Fails with AUR_ERR_INVALID until every parameter has been loaded. */
+int aur_encode(aur_encoder* enc, const int32_t* tokens, const int32_t* cu_seqlens, int32_t n_seq,
+               float* out_f32, uint16_t* out_bf16);
+/* Fused ingest: encode the chunks and append the pooled bf16 vectors to the shard without
+ * leaving the device (insert_chunks, weaviate_client.py:136-212, minus the text handling). */
+int aur_encode_append(aur_encoder* enc, aur_index* ix, const int32_t* tokens,
+                      const int32_t* cu_seqlens, int32_t n_seq, const int64_t* ids,
+                      const int32_t* user_codes, const int32_t* org_codes);
+int aur_encoder_get_stats(aur_encoder* enc, aur_encoder_stats* out);
+
 /* Bring-up / test hooks (not part of the drop-in surface). */
+/* out[M,N] = epi(A[M,K] . W[N,K]^T + bias) through the encoder's tcgen05 GEMM; host buffers,
+ * bf16 bits; epi 0 = bias, 1 = bias + GELU, 2 = bias + resid[M,N]. */
+int aur_debug_gemm(int32_t device, const uint16_t* a, const uint16_t* w, const float* bias,
+                   const uint16_t* resid, int32_t m, int32_t n, int32_t k, int32_t epi,
+                   uint16_t* out, float* ms_out);
+/* ctx[T,H] = self-attention over packed qkv[T,3H] (bf16 bits, host buffers). */
+int aur_debug_attention(int32_t device, const uint16_t* qkv, const int32_t* cu_seqlens,
+                        int32_t n_seq, int32_t heads, int32_t hidden, uint16_t* ctx,
+                        float* ms_out);
+/* Final hidden states [tokens, hidden] (bf16 bits) of the last aur_encode call. */
+int aur_debug_encoder_hidden(aur_encoder* enc, uint16_t* out, int64_t count);
 int aur_debug_tc_scores(aur_index* ix, const void* queries_dev, int32_t nq,
                         int32_t cta_group, float* out_dev /* [n_ctas,128,64] */,
                         int32_t* n_ctas_out, void* stream);
