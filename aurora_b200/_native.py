@@ -103,7 +103,7 @@ def load():
         "aur_encode": (C.c_int, [vp, vp, vp, i32, vp, vp]),
         "aur_encode_append": (C.c_int, [vp, vp, vp, vp, i32, vp, vp, vp]),
         "aur_encoder_get_stats": (C.c_int, [vp, C.POINTER(AurEncoderStats)]),
-        "aur_debug_gemm": (C.c_int, [i32, vp, vp, vp, vp, i32, i32, i32, i32, vp, C.POINTER(C.c_float)]),
+        "aur_debug_gemm": (C.c_int, [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, C.POINTER(C.c_float)]),
         "aur_debug_attention": (C.c_int, [i32, vp, vp, i32, i32, i32, vp, C.POINTER(C.c_float)]),
         "aur_debug_encoder_hidden": (C.c_int, [vp, vp, i64]),
     }

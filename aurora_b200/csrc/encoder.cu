@@ -47,6 +47,7 @@ struct aur_encoder {
   aur_encoder_config cfg{};
   int rows_pad = 0;            // workspace rows (max_tokens rounded up to 128)
   int bn = 256;                // GEMM N tile: 256 when every N divides, else 128
+  int cta_group = 2;           // CTAs per GEMM tile (2: 256-row tiles, the weight tile split over the pair)
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -55,7 +56,8 @@ struct aur_encoder {
   std::vector<Layer> layers;
   std::vector<std::string> missing;   // parameter names not loaded yet
   __nv_bfloat16 *x = nullptr, *y = nullptr, *qkv = nullptr, *ctx = nullptr, *inter = nullptr;
-  CUtensorMap tm_x, tm_ctx, tm_inter, tm_qkv;
+  CUtensorMap tm_x, tm_ctx, tm_inter, tm_qkv;       // loads: box {64, 128}
+  CUtensorMap tmo_qkv, tmo_y, tmo_inter;            // GEMM outputs (TMA store): box {64, 32}
   int32_t *d_tok = nullptr, *d_pos = nullptr, *d_cu = nullptr;
   AttnItem* d_items = nullptr;
   int max_items = 0;
@@ -131,12 +133,13 @@ bool find_param(aur_encoder* e, const std::string& name, ParamSlot* out) {
   return false;
 }
 
-int gemm(aur_encoder* e, const CUtensorMap* tm_a, const CUtensorMap* tm_w, int m_rows, int n, int k, int epi,
-         const float* bias, const __nv_bfloat16* resid, int ldr, __nv_bfloat16* out, int ldo) {
+int gemm(aur_encoder* e, const CUtensorMap* tm_a, const CUtensorMap* tm_w, const CUtensorMap* tm_out, int m_rows, int n,
+         int k, int epi, const float* bias, const __nv_bfloat16* resid, int ldr) {
   GemmParams p{};
-  p.bias = bias; p.resid = resid; p.out = out; p.ldo = ldo; p.ldr = ldr;
-  p.m_tiles = (m_rows + 127) / 128; p.n_tiles = n / e->bn; p.k_blocks = k / 64;
-  ENC_TRY(gemm_tc_launch(e->bn, epi, e->sm_count, tm_a, tm_w, p, e->stream));
+  p.bias = bias; p.resid = resid; p.ldr = ldr;
+  const int tile_m = 128 * e->cta_group;
+  p.m_tiles = (m_rows + tile_m - 1) / tile_m; p.n_tiles = n / e->bn; p.k_blocks = k / 64;
+  ENC_TRY(gemm_tc_launch(e->cta_group, e->bn, epi, e->sm_count, tm_a, tm_w, tm_out, p, e->stream));
   return AUR_OK;
 }
 
@@ -144,7 +147,7 @@ int gemm(aur_encoder* e, const CUtensorMap* tm_a, const CUtensorMap* tm_w, int m
 int forward_locked(aur_encoder* e, const int32_t* cu_host, int n_seq, int n_items) {
   const aur_encoder_config& c = e->cfg;
   const int T = cu_host[n_seq], H = c.hidden, I = c.inter;
-  const int t_pad = round_up(T, 128);
+  const int t_pad = round_up(T, 256);
   cudaStream_t s = e->stream;
   ENC_TRY(cudaMemcpyAsync(e->d_tok, e->h_tok, sizeof(int32_t) * T, cudaMemcpyHostToDevice, s));
   ENC_TRY(cudaMemcpyAsync(e->d_pos, e->h_pos, sizeof(int32_t) * T, cudaMemcpyHostToDevice, s));
@@ -160,12 +163,12 @@ int forward_locked(aur_encoder* e, const int32_t* cu_host, int n_seq, int n_item
   for (int l = 0; l < c.layers; ++l) {
     Layer& L = e->layers[l];
     int rc;
-    if ((rc = gemm(e, &e->tm_x, &L.tm_wqkv, T, 3 * H, H, kEpiBias, L.bqkv, nullptr, 0, e->qkv, 3 * H))) return rc;
+    if ((rc = gemm(e, &e->tm_x, &L.tm_wqkv, &e->tmo_qkv, T, 3 * H, H, kEpiBias, L.bqkv, nullptr, 0))) return rc;
     ENC_TRY(attn_tc_launch(e->sm_count, &e->tm_qkv, ap, s));
-    if ((rc = gemm(e, &e->tm_ctx, &L.tm_wo, T, H, H, kEpiBiasResid, L.bo, e->x, H, e->y, H))) return rc;
+    if ((rc = gemm(e, &e->tm_ctx, &L.tm_wo, &e->tmo_y, T, H, H, kEpiBiasResid, L.bo, e->x, H))) return rc;
     ENC_TRY(launch_layernorm(e->y, L.ln1_g, L.ln1_b, c.ln_eps, T, H, e->x, s));
-    if ((rc = gemm(e, &e->tm_x, &L.tm_wi, T, I, H, kEpiBiasGelu, L.bi, nullptr, 0, e->inter, I))) return rc;
-    if ((rc = gemm(e, &e->tm_inter, &L.tm_wo2, T, H, I, kEpiBiasResid, L.bo2, e->x, H, e->y, H))) return rc;
+    if ((rc = gemm(e, &e->tm_x, &L.tm_wi, &e->tmo_inter, T, I, H, kEpiBiasGelu, L.bi, nullptr, 0))) return rc;
+    if ((rc = gemm(e, &e->tm_inter, &L.tm_wo2, &e->tmo_y, T, H, I, kEpiBiasResid, L.bo2, e->x, H))) return rc;
     ENC_TRY(launch_layernorm(e->y, L.ln2_g, L.ln2_b, c.ln_eps, T, H, e->x, s));
     launches += 7;
   }
@@ -229,7 +232,8 @@ int aur_encoder_open(const aur_encoder_config* cfg, aur_encoder** out) {
   aur_encoder* e = new aur_encoder();
   e->cfg = *cfg;
   e->sm_count = prop.multiProcessorCount;
-  e->rows_pad = round_up(cfg->max_tokens, 128) + 512;   // + one full key window past the last sequence
+  e->rows_pad = round_up(cfg->max_tokens, 256) + 512;   // + one full key window past the last sequence
+  e->cta_group = cfg->reserved == 1 ? 1 : 2;            // reserved = 1 selects the single-CTA GEMM (bring-up)
   e->bn = (H % 256 == 0 && I % 256 == 0) ? 256 : 128;
   e->layers.resize(cfg->layers);
   int rc = AUR_OK;
@@ -261,11 +265,15 @@ int aur_encoder_open(const aur_encoder_config* cfg, aur_encoder** out) {
   // tensor maps: activations are A operands (box 128 rows), weights B operands (box bn rows)
   const int Ri = static_cast<int>(R);
   if ((rc = make_tmap(&e->tm_x, e->x, H, Ri, 128)) || (rc = make_tmap(&e->tm_ctx, e->ctx, H, Ri, 128)) ||
-      (rc = make_tmap(&e->tm_inter, e->inter, I, Ri, 128)) || (rc = make_tmap(&e->tm_qkv, e->qkv, 3 * H, Ri, 128)))
+      (rc = make_tmap(&e->tm_inter, e->inter, I, Ri, 128)) || (rc = make_tmap(&e->tm_qkv, e->qkv, 3 * H, Ri, 128)) ||
+      (rc = make_tmap(&e->tmo_qkv, e->qkv, 3 * H, Ri, 32)) || (rc = make_tmap(&e->tmo_y, e->y, H, Ri, 32)) ||
+      (rc = make_tmap(&e->tmo_inter, e->inter, I, Ri, 32)))
     return fail_open(rc);
   for (Layer& l : e->layers) {
-    if ((rc = make_tmap(&l.tm_wqkv, l.wqkv, H, 3 * H, e->bn)) || (rc = make_tmap(&l.tm_wo, l.wo, H, H, e->bn)) ||
-        (rc = make_tmap(&l.tm_wi, l.wi, H, I, e->bn)) || (rc = make_tmap(&l.tm_wo2, l.wo2, I, H, e->bn)))
+    if ((rc = make_tmap(&l.tm_wqkv, l.wqkv, H, 3 * H, e->bn / e->cta_group)) ||
+        (rc = make_tmap(&l.tm_wo, l.wo, H, H, e->bn / e->cta_group)) ||
+        (rc = make_tmap(&l.tm_wi, l.wi, H, I, e->bn / e->cta_group)) ||
+        (rc = make_tmap(&l.tm_wo2, l.wo2, I, H, e->bn / e->cta_group)))
       return fail_open(rc);
   }
   e->missing = {"word_emb", "pos_emb", "type_emb", "emb_ln_g", "emb_ln_b"};
@@ -367,14 +375,14 @@ int aur_debug_encoder_hidden(aur_encoder* e, uint16_t* out, int64_t count) {
 }
 
 int aur_debug_gemm(int32_t device, const uint16_t* a, const uint16_t* w, const float* bias, const uint16_t* resid,
-                   int32_t m, int32_t n, int32_t k, int32_t epi, uint16_t* out, float* ms_out) {
+                   int32_t m, int32_t n, int32_t k, int32_t epi, int32_t cta_group, uint16_t* out, float* ms_out) {
   if (!a || !w || !bias || !out || m <= 0) return report_error(AUR_ERR_INVALID, "null argument");
-  if (n % 128 || k % 64 || epi < 0 || epi > 2 || (epi == kEpiBiasResid && !resid))
-    return report_error(AUR_ERR_UNSUPPORTED, "n %% 128, k %% 64, epi 0..2");
+  if (n % 128 || k % 64 || epi < 0 || epi > 2 || (epi == kEpiBiasResid && !resid) || (cta_group != 1 && cta_group != 2))
+    return report_error(AUR_ERR_UNSUPPORTED, "n %% 128, k %% 64, epi 0..2, cta_group 1..2");
   ENC_TRY(cudaSetDevice(device));
   cudaDeviceProp prop;
   ENC_TRY(cudaGetDeviceProperties(&prop, device));
-  const int m_pad = round_up(m, 128), bn = n % 256 == 0 ? 256 : 128;
+  const int m_pad = round_up(m, 128 * cta_group), bn = n % 256 == 0 ? 256 : 128;
   __nv_bfloat16 *da = nullptr, *dw = nullptr, *dr = nullptr, *dout = nullptr; float* db = nullptr;
   int rc = AUR_OK;
   auto A = [&](auto** p, size_t cnt) { if (rc == AUR_OK) rc = dev_alloc(p, cnt); };
@@ -386,17 +394,19 @@ int aur_debug_gemm(int32_t device, const uint16_t* a, const uint16_t* w, const f
   cudaMemcpy(dw, w, static_cast<size_t>(n) * k * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(db, bias, sizeof(float) * n, cudaMemcpyHostToDevice);
   if (resid) cudaMemcpy(dr, resid, static_cast<size_t>(m) * n * 2, cudaMemcpyHostToDevice);
-  CUtensorMap tm_a, tm_w;
-  if ((rc = make_tmap(&tm_a, da, k, m_pad, 128)) || (rc = make_tmap(&tm_w, dw, k, n, bn))) return cleanup(rc);
+  CUtensorMap tm_a, tm_w, tm_o;
+  if ((rc = make_tmap(&tm_a, da, k, m_pad, 128)) || (rc = make_tmap(&tm_w, dw, k, n, bn / cta_group)) ||
+      (rc = make_tmap(&tm_o, dout, n, m_pad, 32)))
+    return cleanup(rc);
   GemmParams p{};
-  p.bias = db; p.resid = dr; p.out = dout; p.ldo = n; p.ldr = n;
-  p.m_tiles = m_pad / 128; p.n_tiles = n / bn; p.k_blocks = k / 64;
+  p.bias = db; p.resid = dr; p.ldr = n;
+  p.m_tiles = m_pad / (128 * cta_group); p.n_tiles = n / bn; p.k_blocks = k / 64;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaError_t ce = cudaSuccess;
   for (int rep = 0; rep < 3 && ce == cudaSuccess; ++rep) {   // last repetition is the timed one
     cudaEventRecord(e0, nullptr);
-    ce = gemm_tc_launch(bn, epi, prop.multiProcessorCount, &tm_a, &tm_w, p, nullptr);
+    ce = gemm_tc_launch(cta_group, bn, epi, prop.multiProcessorCount, &tm_a, &tm_w, &tm_o, p, nullptr);
     cudaEventRecord(e1, nullptr);
   }
   if (ce == cudaSuccess) ce = cudaDeviceSynchronize();

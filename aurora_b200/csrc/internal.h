@@ -115,12 +115,11 @@ enum { kEpiBias = 0, kEpiBiasGelu = 1, kEpiBiasResid = 2 };
 struct GemmParams {
   const float* bias;            // [N]
   const __nv_bfloat16* resid;   // [rows, ldr] (kEpiBiasResid only)
-  __nv_bfloat16* out;           // [rows, ldo]
-  int ldo, ldr;
-  int m_tiles, n_tiles, k_blocks;   // 128-row tiles, BN-column tiles, 64-wide k-blocks
+  int ldr;                      // (the output goes through tmap_out: TMA store)
+  int m_tiles, n_tiles, k_blocks;   // (128 * cta_group)-row tiles, BN-column tiles, 64-wide k-blocks
 };
-cudaError_t gemm_tc_launch(int bn, int epi, int sm_count, const void* tmap_a, const void* tmap_b, const GemmParams& p,
-                           cudaStream_t s);
+cudaError_t gemm_tc_launch(int cta_group, int bn, int epi, int sm_count, const void* tmap_a, const void* tmap_b,
+                           const void* tmap_out, const GemmParams& p, cudaStream_t s);
 
 // Self-attention over packed variable-length sequences (<= 512 tokens each), head dim 64.
 // One work item = (sequence, 128-query block); every item runs for all heads.

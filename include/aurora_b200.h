@@ -166,7 +166,7 @@ typedef struct aur_encoder_config {
   int32_t max_tokens;                     /* packed tokens per aur_encode call (workspace)*/
   int32_t max_seqs;                       /* sequences per call                           */
   float   ln_eps;
-  int32_t reserved;
+  int32_t reserved;                       /* 0; (1 = single-CTA GEMM tiles, bring-up only) */
 } aur_encoder_config;
 
 typedef struct aur_encoder_stats {
@@ -199,10 +199,10 @@ int aur_encoder_get_stats(aur_encoder* enc, aur_encoder_stats* out);
 
 /* Bring-up / test hooks (not part of the drop-in surface). */
 /* out[M,N] = epi(A[M,K] . W[N,K]^T + bias) through the encoder's tcgen05 GEMM; host buffers,
- * bf16 bits; epi 0 = bias, 1 = bias + GELU, 2 = bias + resid[M,N]. */
+ * bf16 bits; epi 0 = bias, 1 = bias + GELU, 2 = bias + resid[M,N]; cta_group 1 or 2 (CTAs per tile). */
 int aur_debug_gemm(int32_t device, const uint16_t* a, const uint16_t* w, const float* bias,
                    const uint16_t* resid, int32_t m, int32_t n, int32_t k, int32_t epi,
-                   uint16_t* out, float* ms_out);
+                   int32_t cta_group, uint16_t* out, float* ms_out);
 /* ctx[T,H] = self-attention over packed qkv[T,3H] (bf16 bits, host buffers). */
 int aur_debug_attention(int32_t device, const uint16_t* qkv, const int32_t* cu_seqlens,
                         int32_t n_seq, int32_t heads, int32_t hidden, uint16_t* ctx,

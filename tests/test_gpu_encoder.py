@@ -40,9 +40,10 @@ def _mirror(cfg_o: B.BertConfig) -> EncoderConfig:
 SMALL = B.BertConfig(hidden=128, layers=2, heads=2, inter=256, vocab=120, max_pos=512, pool="cls")
 
 
+@pytest.mark.parametrize("cta_group", [1, 2])
 @pytest.mark.parametrize("m,n,k,epi", [(128, 256, 64, 0), (130, 128, 192, 0), (1000, 768, 768, 2), (777, 3072, 768, 1),
                                        (640, 768, 3072, 2), (500, 384, 384, 1), (1, 256, 64, 0)])
-def test_gemm_matches_numpy(m, n, k, epi):
+def test_gemm_matches_numpy(m, n, k, epi, cta_group):
     lib = N.load()
     rng = np.random.default_rng(m * 7 + n + k + epi)
     a = round_to_bf16(rng.standard_normal((m, k)).astype(np.float32))
@@ -51,7 +52,7 @@ def test_gemm_matches_numpy(m, n, k, epi):
     resid = round_to_bf16(rng.standard_normal((m, n)).astype(np.float32))
     out = np.zeros((m, n), dtype=np.uint16)
     N.check(lib.aur_debug_gemm(0, _ptr(to_bf16_bits(a)), _ptr(to_bf16_bits(w)), _ptr(bias), _ptr(to_bf16_bits(resid)),
-                               m, n, k, epi, _ptr(out), None))
+                               m, n, k, epi, cta_group, _ptr(out), None))
     ref = a.astype(np.float64) @ w.astype(np.float64).T + bias
     if epi == 1:
         ref = B.gelu(ref)
@@ -156,11 +157,11 @@ def test_encode_append_then_search_finds_the_chunk():
     ref = B.encode(cfg_o, w, tok, cu)
     np.testing.assert_array_equal(got_ids[:, 0], ids)
     assert np.all(got_sc[:, 0] > 0.9999)
-    # second-best neighbour agrees with the oracle's embedding geometry
+    # the runner-up's score agrees with the oracle's embedding geometry (random-init embeddings are
+    # all close together, so the runner-up's identity is not stable under bf16 noise; its score is)
     sims = ref @ ref.T
     np.fill_diagonal(sims, -1)
-    agree = (got_ids[:, 1] - 1000 == sims.argmax(axis=1)).mean()
-    assert agree >= 0.9
+    assert np.abs(got_sc[:, 1] - sims.max(axis=1)).max() <= 2e-3
 
 
 def test_encoder_error_paths():

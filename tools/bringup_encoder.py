@@ -30,28 +30,29 @@ def gelu(x):
 def stage_gemm():
     lib = N.load()
     rng = np.random.default_rng(0)
-    for (m, n, k, epi) in [(128, 256, 64, 0), (200, 256, 128, 0), (300, 128, 192, 0), (1000, 768, 768, 2),
+    for g in (1, 2):
+      for (m, n, k, epi) in [(128, 256, 64, 0), (200, 256, 128, 0), (300, 128, 192, 0), (1000, 768, 768, 2),
                            (1000, 2304, 768, 0), (777, 3072, 768, 1), (640, 768, 3072, 2), (500, 384, 384, 1),
-                           (4096, 3072, 768, 1)]:
-        a = round_to_bf16(rng.standard_normal((m, k)).astype(np.float32))
-        w = round_to_bf16((rng.standard_normal((n, k)) / math.sqrt(k)).astype(np.float32))
-        bias = rng.standard_normal(n).astype(np.float32)
-        resid = round_to_bf16(rng.standard_normal((m, n)).astype(np.float32))
-        out = np.zeros((m, n), dtype=np.uint16)
-        ms = C.c_float()
-        N.check(lib.aur_debug_gemm(0, ptr(to_bf16_bits(a)), ptr(to_bf16_bits(w)), ptr(bias), ptr(to_bf16_bits(resid)),
-                                   m, n, k, epi, ptr(out), C.byref(ms)))
-        ref = a.astype(np.float64) @ w.astype(np.float64).T + bias
-        if epi == 1:
-            ref = gelu(ref)
-        if epi == 2:
-            ref = ref + resid
-        got = bf16_bits_to_f32(out).astype(np.float64)
-        err = np.abs(got - ref).max()
-        tol = np.abs(ref).max() * 2 ** -8 + 1e-3
-        tf = 2.0 * m * n * k / (ms.value * 1e-3) / 1e12
-        print(f"gemm m={m} n={n} k={k} epi={epi}: max|err|={err:.4f} (tol {tol:.4f}) {ms.value*1e3:.1f} us {tf:.1f} TF/s", flush=True)
-        assert err <= tol, "GEMM mismatch"
+                           (4096, 3072, 768, 1), (23163, 2304, 768, 0), (23163, 3072, 768, 1), (23163, 768, 3072, 2)]:
+          a = round_to_bf16(rng.standard_normal((m, k)).astype(np.float32))
+          w = round_to_bf16((rng.standard_normal((n, k)) / math.sqrt(k)).astype(np.float32))
+          bias = rng.standard_normal(n).astype(np.float32)
+          resid = round_to_bf16(rng.standard_normal((m, n)).astype(np.float32))
+          out = np.zeros((m, n), dtype=np.uint16)
+          ms = C.c_float()
+          N.check(lib.aur_debug_gemm(0, ptr(to_bf16_bits(a)), ptr(to_bf16_bits(w)), ptr(bias), ptr(to_bf16_bits(resid)),
+                                   m, n, k, epi, g, ptr(out), C.byref(ms)))
+          ref = a.astype(np.float64) @ w.astype(np.float64).T + bias
+          if epi == 1:
+              ref = gelu(ref)
+          if epi == 2:
+              ref = ref + resid
+          got = bf16_bits_to_f32(out).astype(np.float64)
+          err = np.abs(got - ref).max()
+          tol = np.abs(ref).max() * 2 ** -8 + 1e-3
+          tf = 2.0 * m * n * k / (ms.value * 1e-3) / 1e12
+          print(f"gemm g={g} m={m} n={n} k={k} epi={epi}: max|err|={err:.4f} (tol {tol:.4f}) {ms.value*1e3:.1f} us {tf:.1f} TF/s", flush=True)
+          assert err <= tol, "GEMM mismatch"
 
 
 def attn_ref(qkv, cu, heads, hidden):
