@@ -10,7 +10,7 @@
 //                          [64, 128) -- the half of S_0 that is dead once P_0 exists
 //   ctx = O / rowsum       bf16, one 128-byte store per query row and head
 // Warps: 0 TMA producer (Q, K_j, V_j tiles straight out of the packed [tokens, 3H] projection buffer),
-// 1 MMA issuer, 2..5 softmax.  Persistent: items round-robin over the CTAs; the producer runs ahead
+// 1 MMA issuer, 2..9 softmax (two per TMEM lane quarter).  Persistent: items round-robin over the CTAs; the producer runs ahead
 // into the next item as soon as the tensor core has released K (after the S MMAs) and V (after O).
 //
 // Keys past the end of a sequence are masked to -inf before the max, so P is exactly 0 there; the V
@@ -25,6 +25,17 @@
 #include "internal.h"
 #include "ptx.cuh"
 
+#include <stdio.h>
+#ifdef AUR_TC_PROFILE
+#define PROF_DECL(...) long long __VA_ARGS__
+#define PROF_T0() const long long t0_ = clock64()
+#define PROF_ADD(x) x += clock64() - t0_
+#else
+#define PROF_DECL(...)
+#define PROF_T0()
+#define PROF_ADD(x)
+#endif
+
 namespace aur {
 namespace {
 
@@ -32,9 +43,10 @@ using namespace ptx;
 
 constexpr int kQB = 128, kKB = 128, kDh = 64, kMaxKBlocks = 4;
 constexpr int kTileBytes = 128 * kDh * 2;     // 16 KB: 128 rows x 128 B
-constexpr int kAttnThreads = 6 * 32;
+constexpr int kSoftmaxWarps = 8;
+constexpr int kAttnThreads = (2 + kSoftmaxWarps) * 32;
 constexpr int kOCol = 64;                     // O accumulator columns [64, 128)
-constexpr size_t kAttnSmem = 1024 + static_cast<size_t>(1 + 2 * kMaxKBlocks) * kTileBytes + 512;
+constexpr size_t kAttnSmem = 1024 + static_cast<size_t>(1 + 2 * kMaxKBlocks) * kTileBytes + 512 + 512 * 4;
 
 __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -54,6 +66,28 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t d;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
+}
+__device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
+  float m = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
+#pragma unroll
+  for (int e = 2; e < 32; e += 2) m = fmaxf(m, fmaxf(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
+  return m;
+}
+// p_e = 2^(v_e * sc - mc) for 32 scores; packs them as bf16 pairs (the TS-MMA A layout) and returns their sum.
+__device__ __forceinline__ float exp_pack32(const uint32_t (&v)[32], float sc, float mc, uint32_t (&o)[16]) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int e = 0; e < 32; e += 2) {
+    const float p0 = ex2_approx(fmaf(__uint_as_float(v[e]), sc, -mc));
+    const float p1 = ex2_approx(fmaf(__uint_as_float(v[e + 1]), sc, -mc));
+    s0 += p0; s1 += p1;
+    o[e >> 1] = pack_bf16x2(p0, p1);
+  }
+  return s0 + s1;
+}
+// Named barrier shared by the two softmax warps of one TMEM lane quarter (ids 1..4; 0 is __syncthreads).
+__device__ __forceinline__ void pair_sync(int quarter) {
+  asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
 }
 // kind::f16 instruction descriptor with B read MN-major (bit 16): D=f32, A=B=bf16.
 __host__ __device__ constexpr uint32_t idesc_bf16_f32_bmn(int m, int n) {
@@ -78,6 +112,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p)
   uint64_t* bar_o = bars + 18;            // all PV MMAs retired: O complete, V smem reusable
   uint64_t* bar_done = bars + 19;         // softmax warps finished reading O: TMEM reusable
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  float* xch = reinterpret_cast<float*>(bars + 64);   // [2][2][128] partial row max / row sum of the warp pairs
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total = p.n_items * p.heads;
@@ -86,9 +121,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p)
     prefetch_tmap(&tmap_qkv);
     mbar_init(bar_q, 1);
     for (int j = 0; j < kMaxKBlocks; ++j) {
-      mbar_init(&bar_k[j], 1); mbar_init(&bar_v[j], 1); mbar_init(&bar_s[j], 1); mbar_init(&bar_p[j], 4);
+      mbar_init(&bar_k[j], 1); mbar_init(&bar_v[j], 1); mbar_init(&bar_s[j], 1); mbar_init(&bar_p[j], kSoftmaxWarps);
     }
-    mbar_init(bar_qkfree, 1); mbar_init(bar_o, 1); mbar_init(bar_done, 4);
+    mbar_init(bar_qkfree, 1); mbar_init(bar_o, 1); mbar_init(bar_done, kSoftmaxWarps);
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc<1>(tmem_slot, 512); tmem_relinquish<1>(); }
@@ -99,6 +134,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p)
 
   uint32_t blk_phase = 0;   // bit j: parity of the next completion of the per-block barriers j
   int it = 0;
+#ifdef AUR_TC_PROFILE
+  long long pt[4] = {0, 0, 0, 0};
+  const long long pt_begin = clock64();
+#endif
   for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
     const AttnItem item = p.items[w / p.heads];
     const int head = w % p.heads;
@@ -129,12 +168,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p)
       // ---------------------------------------------------------- MMA issuer
       constexpr uint32_t idesc_s = idesc_bf16_f32(kQB, kKB);
       constexpr uint32_t idesc_o = idesc_bf16_f32_bmn(kQB, kDh);
-      if (it > 0) { mbar_wait(bar_done, prev); }
-      mbar_wait(bar_q, par);
+      if (it > 0) { PROF_T0(); mbar_wait(bar_done, prev); PROF_ADD(pt[0]); }
+      { PROF_T0(); mbar_wait(bar_q, par); PROF_ADD(pt[1]); }
       tc_fence_after();
       const uint64_t q_desc = smem_desc_sw128(smem_u32(sQ));
       for (int j = 0; j < nkb; ++j) {
-        mbar_wait(&bar_k[j], (blk_phase >> j) & 1);
+        { PROF_T0(); mbar_wait(&bar_k[j], (blk_phase >> j) & 1); PROF_ADD(pt[1]); }
         tc_fence_after();
         const uint64_t k_desc = smem_desc_sw128(smem_u32(sK + j * kTileBytes));
         if (elect_one()) {
@@ -147,8 +186,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p)
         __syncwarp();
       }
       for (int j = 0; j < nkb; ++j) {
-        mbar_wait(&bar_p[j], (blk_phase >> j) & 1);
-        mbar_wait(&bar_v[j], (blk_phase >> j) & 1);
+        { PROF_T0(); mbar_wait(&bar_p[j], (blk_phase >> j) & 1); PROF_ADD(pt[2]); }
+        { PROF_T0(); mbar_wait(&bar_v[j], (blk_phase >> j) & 1); PROF_ADD(pt[3]); }
         tc_fence_after();
         const uint64_t v_desc = smem_desc_sw128(smem_u32(sV + j * kTileBytes));
         if (elect_one()) {
@@ -161,71 +200,90 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p)
         __syncwarp();
       }
     } else {
-      // ---------------------------------------------------------- softmax (thread = query row)
-      const int quarter = warp & 3;
+      // ---------------------------------------------------------- softmax
+      // Thread = query row; the two warps that share a TMEM lane quarter split every key block's
+      // columns ([0,64) / [64,128)) so each SM sub-partition has two warps to issue from, and
+      // exchange their partial row max / row sum through shared memory.
+      const int quarter = warp & 3, half = (warp - 2) >> 2;
       const int row = quarter * 32 + lane;
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+      const int c0 = half * 64;                    // this warp's first column inside a key block
       float m = -INFINITY;
       for (int j = 0; j < nkb; ++j) {
-        mbar_wait(&bar_s[j], (blk_phase >> j) & 1);
+        { PROF_T0(); mbar_wait(&bar_s[j], (blk_phase >> j) & 1); PROF_ADD(pt[0]); }
         tc_fence_after();
-        const int nvalid = min(kKB, item.len - j * kKB);
-#pragma unroll 1
-        for (int c = 0; c < kKB; c += 32) {
-          if (c >= nvalid) break;
-          uint32_t v[32];
-          tmem_ld_x32(trow + j * kKB + c, v);
-          tmem_wait_ld();
-          if (c + 32 <= nvalid) {
+        const int nv = min(kKB, item.len - j * kKB) - c0;     // valid columns among this warp's 64
+        if (nv <= 0) continue;
+        uint32_t va[32], vb[32];
+        tmem_ld_x32(trow + j * kKB + c0, va);
+        tmem_ld_x32(trow + j * kKB + c0 + 32, vb);
+        tmem_wait_ld();
+        if (nv >= 64) {
+          m = fmaxf(m, fmaxf(max32(va), max32(vb)));
+        } else {
 #pragma unroll
-            for (int e = 0; e < 32; e += 2) m = fmaxf(m, fmaxf(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) if (c + e < nvalid) m = fmaxf(m, __uint_as_float(v[e]));
+          for (int e = 0; e < 32; ++e) {
+            if (e < nv) m = fmaxf(m, __uint_as_float(va[e]));
+            if (32 + e < nv) m = fmaxf(m, __uint_as_float(vb[e]));
           }
         }
       }
-      const float mc = m * p.scale_log2e;
+      xch[half * 128 + row] = m;
+      { PROF_T0(); pair_sync(quarter); PROF_ADD(pt[1]); }
+      m = fmaxf(m, xch[(half ^ 1) * 128 + row]);   // >= one valid key per sequence: finite
+      const float sc = p.scale_log2e, mc = m * sc;
       float sum = 0.f;
       for (int j = 0; j < nkb; ++j) {
-        const int nvalid = min(kKB, item.len - j * kKB);
-#pragma unroll 1
-        for (int c = 0; c < kKB; c += 32) {
-          uint32_t o[16];
-          if (c < nvalid) {
-            uint32_t v[32];
-            tmem_ld_x32(trow + j * kKB + c, v);
-            tmem_wait_ld();
-#pragma unroll
-            for (int e = 0; e < 32; e += 2) {
-              float p0 = ex2_approx(fmaf(__uint_as_float(v[e]), p.scale_log2e, -mc));
-              float p1 = ex2_approx(fmaf(__uint_as_float(v[e + 1]), p.scale_log2e, -mc));
-              if (c + e >= nvalid) p0 = 0.f;
-              if (c + e + 1 >= nvalid) p1 = 0.f;
-              sum += p0 + p1;
-              o[e >> 1] = pack_bf16x2(p0, p1);
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) o[e] = 0u;
-          }
-          tmem_st_x16(trow + j * kKB + (c >> 1), o);
+        const int nv = min(kKB, item.len - j * kKB) - c0;
+        const uint32_t tblk = trow + j * kKB;
+        uint32_t va[32], vb[32], oa[16], ob[16];
+        if (nv > 0) {
+          tmem_ld_x32(tblk + c0, va);
+          tmem_ld_x32(tblk + c0 + 32, vb);
+          tmem_wait_ld();
         }
+        // P_j lands on columns [0,64) of S_j, i.e. on scores the other warp of the pair reads: both
+        // must hold their scores in registers before either writes
+        { PROF_T0(); pair_sync(quarter); PROF_ADD(pt[1]); }
+        PROF_T0();
+        if (nv >= 64) {
+          sum += exp_pack32(va, sc, mc, oa) + exp_pack32(vb, sc, mc, ob);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+            if (e < nv) p0 = ex2_approx(fmaf(__uint_as_float(va[e]), sc, -mc));
+            if (e + 1 < nv) p1 = ex2_approx(fmaf(__uint_as_float(va[e + 1]), sc, -mc));
+            if (32 + e < nv) p2 = ex2_approx(fmaf(__uint_as_float(vb[e]), sc, -mc));
+            if (33 + e < nv) p3 = ex2_approx(fmaf(__uint_as_float(vb[e + 1]), sc, -mc));
+            sum += (p0 + p1) + (p2 + p3);
+            oa[e >> 1] = pack_bf16x2(p0, p1); ob[e >> 1] = pack_bf16x2(p2, p3);
+          }
+        }
+        tmem_st_x16(tblk + (c0 >> 1), oa);
+        tmem_st_x16(tblk + (c0 >> 1) + 16, ob);
         tmem_wait_st();
+        PROF_ADD(pt[2]);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_p[j]);
       }
-      mbar_wait(bar_o, par);
+      xch[256 + half * 128 + row] = sum;
+      pair_sync(quarter);
+      sum += xch[256 + (half ^ 1) * 128 + row];
+      { PROF_T0(); mbar_wait(bar_o, par); PROF_ADD(pt[3]); }
       tc_fence_after();
       const float inv = 1.0f / sum;
       const bool live = item.q0 + row < item.len;
-      __nv_bfloat16* dst = p.ctx + static_cast<size_t>(item.tok0 + item.q0 + row) * p.ld_ctx + head * kDh;
-#pragma unroll
-      for (int c = 0; c < kDh; c += 32) {
+      __nv_bfloat16* dst = p.ctx + static_cast<size_t>(item.tok0 + item.q0 + row) * p.ld_ctx + head * kDh + half * 32;
+      {
         uint32_t v[32];
-        tmem_ld_x32(trow + kOCol + c, v);
+        tmem_ld_x32(trow + kOCol + half * 32, v);
         tmem_wait_ld();
+        // O is in registers: hand TMEM to the next item's S MMAs before the global stores
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_done);
         if (live) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -234,16 +292,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p)
             q4.y = pack_bf16x2(__uint_as_float(v[8 * e + 2]) * inv, __uint_as_float(v[8 * e + 3]) * inv);
             q4.z = pack_bf16x2(__uint_as_float(v[8 * e + 4]) * inv, __uint_as_float(v[8 * e + 5]) * inv);
             q4.w = pack_bf16x2(__uint_as_float(v[8 * e + 6]) * inv, __uint_as_float(v[8 * e + 7]) * inv);
-            reinterpret_cast<uint4*>(dst + c)[e] = q4;
+            reinterpret_cast<uint4*>(dst)[e] = q4;
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_done);
     }
     blk_phase ^= (1u << nkb) - 1u;
   }
+#ifdef AUR_TC_PROFILE
+  if (blockIdx.x == 0 && lane == 0 && (warp == 1 || warp == 2 || warp == 6))
+    printf("attn prof warp %d items %d total %lld : %lld %lld %lld %lld  (mma: done,qk,p,v | softmax: wait_s,pair_sync,pass2,wait_o)\n",
+           warp, it, clock64() - pt_begin, pt[0], pt[1], pt[2], pt[3]);
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc<1>(tmem_base, 512); }

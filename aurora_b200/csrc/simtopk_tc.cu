@@ -47,6 +47,14 @@
 #include "internal.h"
 #include "ptx.cuh"
 
+// Bring-up timers compile to nothing unless the library is built with AUR_TC_PROFILE=1: every
+// clock64() is a scheduling barrier inside the hot loops.
+#ifdef AUR_TC_PROFILE
+#define TCLK() clock64()
+#else
+#define TCLK() 0ll
+#endif
+
 namespace aur {
 using namespace ptx;
 
@@ -295,22 +303,22 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       constexpr uint32_t kBox16 = ((kTcTileN / kCtaGroup) * 128u) >> 4;  // box stride in descriptor units
       int stage = 0; uint32_t phase = 0;
       long long tm_empty = 0, tm_full = 0;
-      const long long tm_begin = clock64();
+      const long long tm_begin = TCLK();
       for (int it = 0; it < my_tiles; ++it) {
         const int b = it & 1;
         {
-          const long long t0 = clock64();
+          const long long t0 = TCLK();
           mbar_wait(&tmem_empty[b], ((static_cast<uint32_t>(it) >> 1) & 1u) ^ 1u);
-          tm_empty += clock64() - t0;
+          tm_empty += TCLK() - t0;
         }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + kTcAccCol0 + b * kTcTileN;
         for (int kb0 = 0; kb0 < kbs; kb0 += kTcKbPerStage) {
           const int nkb = min(kTcKbPerStage, kbs - kb0);
           {
-            const long long t0 = clock64();
+            const long long t0 = TCLK();
             mbar_wait(&full_bar[stage], phase);
-            tm_full += clock64() - t0;
+            tm_full += TCLK() - t0;
           }
           tc_fence_after();
           const uint32_t base_lo = (smem_u32(smem + static_cast<uint32_t>(stage) * L.stage_bytes) & 0x3FFFFu) >> 4;
@@ -337,7 +345,7 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       if ((p.dbg_flags & 64) && p.dbg_scores != nullptr && lane == 0) {
         float* d = p.dbg_scores + static_cast<size_t>(blockIdx.x) * kTcQRows * kTcTileN + 32;
         d[0] = static_cast<float>(tm_empty); d[1] = static_cast<float>(tm_full);
-        d[2] = static_cast<float>(clock64() - tm_begin);
+        d[2] = static_cast<float>(TCLK() - tm_begin);
       }
     }
   } else {
@@ -376,7 +384,7 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     } else {
       // ============================== epilogue warps ==============================
       const int grp = (warp - kThrWarps) >> 2;   // epilogue group: takes tiles grp, grp + groups, ...
-      const long long t_kernel0 = clock64();
+      const long long t_kernel0 = TCLK();
       // ---- park this thread's query row in TMEM (bf16 pairs, K ascending along columns);
       //      with two groups each loads every other k-block
       {
@@ -408,7 +416,7 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       float published = -INFINITY;
       int nslow = 0;
       long long t_wait = 0, t_slow = 0, t_ld = 0, t_top = 0, t_fast = 0, t_chunks = 0, t_pub = 0;
-      const long long t_begin = clock64();
+      const long long t_begin = TCLK();
       long long t_boot = 0, t_loop_end = 0;
 
       // inverse norms: tile(0) into buffer 0, tile(1) in flight in registers
@@ -460,7 +468,7 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
           tboot = read_threshold(thr_q, p.epoch);
         } while (__any_sync(0xffffffffu, tboot == -INFINITY) && clock64() - tb < 100000);
         st.tau = fmaxf(st.tau, tboot);
-        t_boot = clock64() - t_begin;
+        t_boot = TCLK() - t_begin;
       }
 
       int li = 0;  // this group's iteration count
@@ -469,7 +477,7 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         const int row0 = tile * kTcTileN;
         const int b = it & 1;
         const float* nb = mynorm + (li & 1) * kTcTileN;
-        const long long t_top0 = clock64();
+        const long long t_top0 = TCLK();
         const unsigned long long thr_e = xchg ? __ldcg(thr_q) : 0ull;   // consumed after the fast path
 
         // norms of the next tile (loaded one iteration ago) -> the other buffer; start the
@@ -482,12 +490,12 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         }
 
         {
-          const long long t0 = clock64();
+          const long long t0 = TCLK();
           mbar_wait(&tmem_full[b], (static_cast<uint32_t>(it) >> 1) & 1u);
-          t_wait += clock64() - t0;
+          t_wait += TCLK() - t0;
         }
         tc_fence_after();
-        const long long t_ld0 = clock64();
+        const long long t_ld0 = TCLK();
         uint32_t acc[4][16];
         if (!(p.dbg_flags & 1)) {
 #pragma unroll
@@ -499,9 +507,9 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         if (lane == 0) {  // accumulator drained into registers: hand the buffer back to the MMA warp
           if constexpr (kCtaGroup == 2) mbar_arrive_cluster(&tmem_empty[b], 0); else mbar_arrive(&tmem_empty[b]);
         }
-        t_ld += clock64() - t_ld0;
+        t_ld += TCLK() - t_ld0;
         if (p.dbg_flags & 1) continue;
-        const long long t_fast0 = clock64();
+        const long long t_fast0 = TCLK();
 
         // Fast path: scale by 1/|c_j| in place (packed FMUL2) and keep one running max per 16
         // scores.  (NaN norm = tombstone / out of range: fmaxf drops it, `>=` rejects it.)
@@ -530,14 +538,14 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
                   __uint_as_float(acc[c][j]);
         }
 
-        t_fast += clock64() - t_fast0;
-        const long long t_ch0 = clock64();
+        t_fast += TCLK() - t_fast0;
+        const long long t_ch0 = TCLK();
         // A group of four scores whose max reaches this query's threshold goes out of line.
         if (static_cast<uint32_t>(thr_e >> 32) == p.epoch) st.tau = fmaxf(st.tau, __uint_as_float(static_cast<uint32_t>(thr_e)));
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           if (cmax[c] >= st.tau) {
-            const long long t0 = clock64();
+            const long long t0 = TCLK();
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               const float s0 = __uint_as_float(acc[c][4 * g]), s1 = __uint_as_float(acc[c][4 * g + 1]);
@@ -546,21 +554,21 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
                 st = push_group4(st, s0, s1, s2, s3, row0 + c * 16 + 4 * g, list_a, ksel);
             }
             ++nslow;
-            t_slow += clock64() - t0;
+            t_slow += TCLK() - t0;
           }
         }
 
-        if (li < 8) t_top += clock64() - t_ch0; else t_chunks += clock64() - t_ch0;   // t_top reused: early tiles
-        const long long t_pub0 = clock64();
+        if (li < 8) t_top += TCLK() - t_ch0; else t_chunks += TCLK() - t_ch0;   // t_top reused: early tiles
+        const long long t_pub0 = TCLK();
         // publish this CTA's m-th best for the exchange (monotone, so stale reads stay valid)
         const float pv = (xm == 1) ? st.top1 : st.top2;
         if (xchg && pv > published) {
           published = pv;
           atomicMax(pubrow + tset, (static_cast<unsigned long long>(p.epoch) << 32) | f32_to_ord(pv));
         }
-        t_pub += clock64() - t_pub0;
+        t_pub += TCLK() - t_pub0;
       }
-      t_loop_end = clock64();
+      t_loop_end = TCLK();
       __syncwarp();
       if (lane == 0) atomicAdd(const_cast<int*>(epi_done), 1);   // lets the threshold warps go
 
@@ -584,11 +592,11 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         d[2] = tau_end; d[3] = st.tau_local;
         d[8] = static_cast<float>(t_wait); d[9] = static_cast<float>(t_slow);
         d[10] = 0.f; d[11] = static_cast<float>(t_ld);
-        d[12] = static_cast<float>(clock64() - t_begin);
+        d[12] = static_cast<float>(TCLK() - t_begin);
         d[13] = static_cast<float>(t_top); d[14] = static_cast<float>(t_fast);
         d[15] = static_cast<float>(t_chunks); d[16] = static_cast<float>(t_pub);
         d[17] = static_cast<float>(t_boot); d[18] = static_cast<float>(t_begin - t_kernel0);
-        d[19] = static_cast<float>(clock64() - t_loop_end);
+        d[19] = static_cast<float>(TCLK() - t_loop_end);
       }
     }
   }
