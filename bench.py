@@ -324,10 +324,94 @@ def run_ours(args):
             "reference_pure_python_queries_per_s": cpu_pure_python_qps(),
             "note": "Weaviate 1.27.6 / t2v containers cannot run here; oracle fp32 flat cosine search on all host cores",
         }
+        if not args.no_encoder:
+            ix.close()
+            torch.cuda.empty_cache()
+            out["encoder"] = encoder_leg(local)
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def encoder_leg(device: int) -> dict:
+    """Second hot-path row (BASELINE.json configs[2] shape): bge-base-en
+    dimensions, random-init bf16 weights, cfg3 chunk lengths ~N(384, 96) clipped to [16, 512].
+    Device time of the forward (CUDA events inside the library), the same call end to end with
+    host token ids in / host vectors out, and transformers' BertModel on the host cores beside it."""
+    from aurora_b200.encoder import Encoder, EncoderConfig
+
+    cfg = EncoderConfig()
+    rng = np.random.default_rng(1003)
+    n_seq = 192
+    lens = np.clip(np.rint(rng.normal(384, 96, n_seq)), 16, 512).astype(np.int64)
+    cu = np.zeros(n_seq + 1, np.int32)
+    cu[1:] = np.cumsum(lens)
+    tok = rng.integers(1000, cfg.vocab, size=int(cu[-1])).astype(np.int32)
+    tok[cu[:-1]] = 101
+    tok[cu[1:] - 1] = 102
+    h, i = cfg.hidden, cfg.inter
+    shapes = {"word_emb": (cfg.vocab, h), "pos_emb": (cfg.max_pos, h), "type_emb": (cfg.type_vocab, h),
+              "emb_ln_g": (h,), "emb_ln_b": (h,)}
+    for l in range(cfg.layers):
+        for k, shp in {"wqkv": (3 * h, h), "bqkv": (3 * h,), "wo": (h, h), "bo": (h,), "ln1_g": (h,), "ln1_b": (h,),
+                       "wi": (i, h), "bi": (i,), "wo2": (h, i), "bo2": (h,), "ln2_g": (h,), "ln2_b": (h,)}.items():
+            shapes[f"l{l}.{k}"] = shp
+    wrng = np.random.default_rng(7)
+    with Encoder(cfg, max_tokens=int(cu[-1]) + 256, max_seqs=n_seq, device=device) as enc:
+        for name, shp in shapes.items():
+            a = (1.0 + 0.1 * wrng.standard_normal(shp)) if name.endswith("_g") else 0.02 * wrng.standard_normal(shp)
+            enc.load_weights({name: a.astype(np.float32)})
+        for _ in range(3):
+            enc.encode_packed(tok, cu)
+        dev_ms, e2e_ms = [], []
+        for _ in range(10):
+            t0 = time.perf_counter()
+            enc.encode_packed(tok, cu)
+            e2e_ms.append((time.perf_counter() - t0) * 1e3)
+            dev_ms.append(enc.stats()["total_ms"])
+        st = enc.stats()
+    ms, ems = float(np.median(dev_ms)), float(np.median(e2e_ms))
+    flops = st["gemm_flops"] + st["attn_flops"]
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak_tf, peak_src = float(json.load(f)["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    except Exception:
+        peak_tf, peak_src = 1500.0, "fallback (B200_PROFILING.md)"
+    out = {
+        "workload": "bge-base-en dims (H768 L12 A12 I3072), random-init bf16, 192 chunks, lengths ~N(384,96) in [16,512]",
+        "chunks": n_seq, "tokens": int(st["tokens"]), "ms_per_batch": ms, "chunks_per_s": n_seq / (ms * 1e-3),
+        "tokens_per_s": st["tokens"] / (ms * 1e-3), "gpu_launches_per_batch": int(st["launches"]),
+        "flops_per_batch": flops, "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peak_tf,
+                                               "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / peak_tf,
+                                               "peak_source": peak_src,
+                                               "note": "whole forward (GEMMs + attention + LayerNorm + pooling) over real (unpadded) tokens"},
+        "e2e": {"chunks_per_s": n_seq / (ems * 1e-3), "ms_per_batch": ems, "h2d_bytes_per_batch": int(tok.nbytes + cu.nbytes),
+                "d2h_bytes_per_batch": n_seq * h * 4},
+    }
+    try:   # host baseline: the class the reference's t2v sidecar runs, fp32, all host cores
+        import torch
+        from transformers import BertConfig as HFConfig, BertModel
+
+        n_cpu = 16
+        hf = BertModel(HFConfig(vocab_size=cfg.vocab, hidden_size=h, num_hidden_layers=cfg.layers, num_attention_heads=cfg.heads,
+                                intermediate_size=i, max_position_embeddings=cfg.max_pos), add_pooling_layer=False).eval()
+        smax = int(lens[:n_cpu].max())
+        ids = np.zeros((n_cpu, smax), np.int64)
+        mask = np.zeros((n_cpu, smax), np.int64)
+        for s_ in range(n_cpu):
+            ids[s_, :lens[s_]] = tok[cu[s_]:cu[s_ + 1]]
+            mask[s_, :lens[s_]] = 1
+        with torch.no_grad():
+            hf(input_ids=torch.from_numpy(ids[:2]), attention_mask=torch.from_numpy(mask[:2]))
+            t0 = time.perf_counter()
+            hf(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask))
+            dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n_cpu / dt, "unit": "chunks/s", "cores": os.cpu_count() or 1, "kind": "reference-stack",
+                               "sample": f"{n_cpu} chunks, transformers.BertModel fp32 (torch {torch.get_num_threads()} threads), one padded batch ({dt:.2f} s)"}
+    except Exception as e:   # transformers missing: report, do not fail the search line
+        out["cpu_baseline"] = {"unavailable": str(e)[:120]}
+    return out
 
 
 def main():
@@ -336,6 +420,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-encoder", action="store_true", help="skip the encoder leg of the N=1 run")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
