@@ -152,6 +152,33 @@ class Encoder:
         return out
 
 
+class TextEncoder:
+    """Adapter for aurora_b200.retriever.KnowledgeBase: ``dim`` + ``encode(texts)`` over a tokenizer
+    callable and the CUDA ``Encoder``; ``encode_append`` is the fused ingest path (vectors never
+    leave the device between the forward pass and the shard append)."""
+
+    def __init__(self, encoder: Encoder, tokenize: Callable[[str], List[int]]):
+        self._enc, self._tok = encoder, tokenize
+        self.dim = encoder.cfg.hidden
+
+    def encode(self, texts: Sequence[str]) -> np.ndarray:
+        return self._enc.encode([self._tok(t) for t in texts])
+
+    def encode_append(self, index, texts: Sequence[str], ids: np.ndarray, user_codes=None, org_codes=None) -> None:
+        seqs = [self._tok(t) for t in texts]
+        i = 0
+        while i < len(seqs):
+            j, toks = i, 0
+            while j < len(seqs) and j - i < self._enc.max_seqs and toks + len(seqs[j]) <= self._enc.max_tokens:
+                toks += len(seqs[j]); j += 1
+            if j == i:
+                raise ValueError(f"text {i} tokenizes to {len(seqs[i])} tokens: more than max_tokens={self._enc.max_tokens}")
+            tok, cu = pack_sequences(seqs[i:j])
+            self._enc.encode_append(index, tok, cu, ids[i:j], None if user_codes is None else user_codes[i:j],
+                                    None if org_codes is None else org_codes[i:j])
+            i = j
+
+
 # ----------------------------------------------------------------------------- reference mirror
 class EmbeddingClient:
     """Drop-in for server/services/correlation/embedding_client.py:20-78 backed by ``Encoder``."""

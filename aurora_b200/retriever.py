@@ -113,7 +113,8 @@ class KnowledgeBase:
                 logger.error(f"[KB B200] Error adding chunk: {e}")
         if not metas:
             return 0
-        vecs = self.encoder.encode(texts)
+        fused = hasattr(self.encoder, "encode_append") and hasattr(self.index, "_h")   # CUDA encoder + CUDA shard
+        vecs = None if fused else self.encoder.encode(texts)
         with self._lock:
             ids = np.empty(len(metas), dtype=np.int64)
             for i, (key, _) in enumerate(metas):
@@ -123,7 +124,10 @@ class KnowledgeBase:
                 ids[i] = self._key2id[key]
             ucode = np.full(len(metas), self._code(self._user_code, user_id, True), dtype=np.int32)
             ocode = np.full(len(metas), self._code(self._org_code, org_id, True), dtype=np.int32)
-            self.index.add(vecs, ids, ucode, ocode)
+            if fused:
+                self.encoder.encode_append(self.index, texts, ids, ucode, ocode)
+            else:
+                self.index.add(vecs, ids, ucode, ocode)
             for i, (_, props) in enumerate(metas):
                 self._props[int(ids[i])] = props
         return len(metas)

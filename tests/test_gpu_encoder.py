@@ -204,3 +204,33 @@ def test_embedding_client_mirror():
     assert batch[1] is None and batch[0] == v and len(batch[2]) == cfg_o.hidden
     client.close()
     assert client.embed("after close") is None                           # any failure -> None (:66-70)
+
+
+def test_retriever_with_cuda_encoder_end_to_end():
+    """search_knowledge_base / insert_chunks (weaviate_client.py:136-285 signatures) running on the
+    CUDA encoder + CUDA shard, fused ingest included."""
+    from aurora_b200 import retriever as R
+    from aurora_b200.encoder import TextEncoder
+
+    cfg_o = SMALL
+    enc = Encoder(_mirror(cfg_o), max_tokens=4096, max_seqs=64)
+    enc.load_weights(B.init_weights(cfg_o, seed=7, bf16=True))
+    vocab = {}
+    tokenize = lambda t: [1] + [vocab.setdefault(w, 3 + len(vocab) % 110) for w in t.lower().split()][:100] + [2]
+    R.configure(encoder=TextEncoder(enc, tokenize), capacity=1024, device=0)
+    try:
+        chunks = [{"content": f"runbook step {i}: restart service alpha-{i} and check queue depth", "heading_context": "Recovery",
+                   "chunk_index": i} for i in range(12)]
+        assert R.insert_chunks("u1", "doc1", "runbook.md", chunks, org_id="o1") == 12
+        assert R.insert_chunks("u2", "doc2", "other.md", [{"content": "unrelated billing notes", "chunk_index": 0}]) == 1
+        assert R.get_document_chunk_count("u1", "doc1") == 12
+        hits = R.search_knowledge_base("u1", "Recovery\nrunbook step 7: restart service alpha-7 and check queue depth", limit=3)
+        assert hits and hits[0]["chunk_index"] == 7 and hits[0]["document_id"] == "doc1" and hits[0]["score"] > 0.999
+        assert set(hits[0]) == {"content", "heading_context", "source_filename", "document_id", "chunk_index", "score"}
+        assert all(h["document_id"] == "doc1" for h in R.search_knowledge_base("u1", "billing", limit=5))   # tenant scope
+        assert R.search_knowledge_base("u1", "   ") == []
+        assert R.delete_document_chunks("u1", "doc1") == 12
+        assert R.search_knowledge_base("u1", "runbook step 7", limit=3) == []
+    finally:
+        R.configure(encoder=None)
+        enc.close()
