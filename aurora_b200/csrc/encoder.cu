@@ -48,6 +48,8 @@ struct aur_encoder {
   int rows_pad = 0;            // workspace rows (max_tokens rounded up to 128)
   int bn = 256;                // GEMM N tile: 256 when every N divides, else 128
   int cta_group = 2;           // CTAs per GEMM tile (2: 256-row tiles, the weight tile split over the pair)
+  int dh = 64;                 // real head dim (64, or 32 zero-padded to 64 inside the qkv / ctx layout)
+  int hp = 0;                  // heads * 64: width of each of q, k, v in the qkv buffer and of ctx
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -103,33 +105,35 @@ void free_all(aur_encoder* e) {
   if (e->stream) cudaStreamDestroy(e->stream);
 }
 
-struct ParamSlot { void* dst; int64_t count; bool bf16; };
+// pad: 0 none; 1 rows are [3][heads][dh] -> [3][heads][64] (wqkv / bqkv); 2 columns are [heads][dh] -> [heads][64] (wo)
+struct ParamSlot { void* dst; int64_t count; bool bf16; int pad; };
 
 // Resolve a parameter name to its device buffer.
 bool find_param(aur_encoder* e, const std::string& name, ParamSlot* out) {
   const aur_encoder_config& c = e->cfg;
   const int64_t H = c.hidden, I = c.inter;
-  if (name == "word_emb") { *out = {e->word, static_cast<int64_t>(c.vocab) * H, true}; return true; }
-  if (name == "pos_emb") { *out = {e->pos, static_cast<int64_t>(c.max_pos) * H, true}; return true; }
-  if (name == "type_emb") { *out = {e->type, static_cast<int64_t>(c.type_vocab) * H, true}; return true; }
-  if (name == "emb_ln_g") { *out = {e->emb_g, H, false}; return true; }
-  if (name == "emb_ln_b") { *out = {e->emb_b, H, false}; return true; }
+  if (name == "word_emb") { *out = {e->word, static_cast<int64_t>(c.vocab) * H, true, 0}; return true; }
+  if (name == "pos_emb") { *out = {e->pos, static_cast<int64_t>(c.max_pos) * H, true, 0}; return true; }
+  if (name == "type_emb") { *out = {e->type, static_cast<int64_t>(c.type_vocab) * H, true, 0}; return true; }
+  if (name == "emb_ln_g") { *out = {e->emb_g, H, false, 0}; return true; }
+  if (name == "emb_ln_b") { *out = {e->emb_b, H, false, 0}; return true; }
   int l = -1; char leaf[32] = {0};
   if (sscanf(name.c_str(), "l%d.%31s", &l, leaf) != 2 || l < 0 || l >= c.layers) return false;
   Layer& L = e->layers[l];
   const std::string f = leaf;
-  if (f == "wqkv") { *out = {L.wqkv, 3 * H * H, true}; return true; }
-  if (f == "wo") { *out = {L.wo, H * H, true}; return true; }
-  if (f == "wi") { *out = {L.wi, I * H, true}; return true; }
-  if (f == "wo2") { *out = {L.wo2, H * I, true}; return true; }
-  if (f == "bqkv") { *out = {L.bqkv, 3 * H, false}; return true; }
-  if (f == "bo") { *out = {L.bo, H, false}; return true; }
-  if (f == "bi") { *out = {L.bi, I, false}; return true; }
-  if (f == "bo2") { *out = {L.bo2, H, false}; return true; }
-  if (f == "ln1_g") { *out = {L.ln1_g, H, false}; return true; }
-  if (f == "ln1_b") { *out = {L.ln1_b, H, false}; return true; }
-  if (f == "ln2_g") { *out = {L.ln2_g, H, false}; return true; }
-  if (f == "ln2_b") { *out = {L.ln2_b, H, false}; return true; }
+  const int padded = e->dh != 64;
+  if (f == "wqkv") { *out = {L.wqkv, 3 * H * H, true, padded ? 1 : 0}; return true; }
+  if (f == "wo") { *out = {L.wo, H * H, true, padded ? 2 : 0}; return true; }
+  if (f == "wi") { *out = {L.wi, I * H, true, 0}; return true; }
+  if (f == "wo2") { *out = {L.wo2, H * I, true, 0}; return true; }
+  if (f == "bqkv") { *out = {L.bqkv, 3 * H, false, padded ? 1 : 0}; return true; }
+  if (f == "bo") { *out = {L.bo, H, false, 0}; return true; }
+  if (f == "bi") { *out = {L.bi, I, false, 0}; return true; }
+  if (f == "bo2") { *out = {L.bo2, H, false, 0}; return true; }
+  if (f == "ln1_g") { *out = {L.ln1_g, H, false, 0}; return true; }
+  if (f == "ln1_b") { *out = {L.ln1_b, H, false, 0}; return true; }
+  if (f == "ln2_g") { *out = {L.ln2_g, H, false, 0}; return true; }
+  if (f == "ln2_b") { *out = {L.ln2_b, H, false, 0}; return true; }
   return false;
 }
 
@@ -158,14 +162,15 @@ int forward_locked(aur_encoder* e, const int32_t* cu_host, int n_seq, int n_item
   ENC_TRY(launch_embed_ln(e->d_tok, e->d_pos, T, t_pad, e->word, e->pos, e->type, e->emb_g, e->emb_b, c.ln_eps, H, e->x, s));
   ++launches;
   AttnParams ap{};
-  ap.items = e->d_items; ap.n_items = n_items; ap.heads = c.heads; ap.hidden = H; ap.ctx = e->ctx; ap.ld_ctx = H;
-  ap.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(H / c.heads));
+  const int HP = e->hp;
+  ap.items = e->d_items; ap.n_items = n_items; ap.heads = c.heads; ap.hidden = HP; ap.ctx = e->ctx; ap.ld_ctx = HP;
+  ap.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(e->dh));
   for (int l = 0; l < c.layers; ++l) {
     Layer& L = e->layers[l];
     int rc;
-    if ((rc = gemm(e, &e->tm_x, &L.tm_wqkv, &e->tmo_qkv, T, 3 * H, H, kEpiBias, L.bqkv, nullptr, 0))) return rc;
+    if ((rc = gemm(e, &e->tm_x, &L.tm_wqkv, &e->tmo_qkv, T, 3 * HP, H, kEpiBias, L.bqkv, nullptr, 0))) return rc;
     ENC_TRY(attn_tc_launch(e->sm_count, &e->tm_qkv, ap, s));
-    if ((rc = gemm(e, &e->tm_ctx, &L.tm_wo, &e->tmo_y, T, H, H, kEpiBiasResid, L.bo, e->x, H))) return rc;
+    if ((rc = gemm(e, &e->tm_ctx, &L.tm_wo, &e->tmo_y, T, H, HP, kEpiBiasResid, L.bo, e->x, H))) return rc;
     ENC_TRY(launch_layernorm(e->y, L.ln1_g, L.ln1_b, c.ln_eps, T, H, e->x, s));
     if ((rc = gemm(e, &e->tm_x, &L.tm_wi, &e->tmo_inter, T, I, H, kEpiBiasGelu, L.bi, nullptr, 0))) return rc;
     if ((rc = gemm(e, &e->tm_inter, &L.tm_wo2, &e->tmo_y, T, H, I, kEpiBiasResid, L.bo2, e->x, H))) return rc;
@@ -179,7 +184,7 @@ int forward_locked(aur_encoder* e, const int32_t* cu_host, int n_seq, int n_item
   double af = 0.0;
   for (int i = 0; i < n_seq; ++i) { const double len = cu_host[i + 1] - cu_host[i]; af += 4.0 * len * len * H; }
   e->stats.attn_flops = af * c.layers;
-  e->stats.gemm_flops = 2.0 * T * (3.0 * H * H + 1.0 * H * H + 2.0 * H * I) * c.layers;
+  e->stats.gemm_flops = 2.0 * T * (3.0 * H * H + 1.0 * H * H + 2.0 * H * I) * c.layers;   // algorithmic (unpadded heads)
   e->last_tokens = T;
   return AUR_OK;
 }
@@ -219,8 +224,8 @@ int aur_encoder_open(const aur_encoder_config* cfg, aur_encoder** out) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return report_error(AUR_ERR_NO_DEVICE, "no CUDA device: aurora_b200 has no CPU path");
   if (cfg->device < 0 || cfg->device >= ndev) return report_error(AUR_ERR_INVALID, "device %d of %d", cfg->device, ndev);
   const int H = cfg->hidden, I = cfg->inter;
-  if (H <= 0 || cfg->heads <= 0 || H % cfg->heads || H / cfg->heads != 64)
-    return report_error(AUR_ERR_UNSUPPORTED, "head dim must be 64 (hidden %d, heads %d)", H, cfg->heads);
+  if (H <= 0 || cfg->heads <= 0 || H % cfg->heads || (H / cfg->heads != 64 && H / cfg->heads != 32))
+    return report_error(AUR_ERR_UNSUPPORTED, "head dim must be 64 or 32 (hidden %d, heads %d)", H, cfg->heads);
   if (H % 128 || I % 128 || H > 1024) return report_error(AUR_ERR_UNSUPPORTED, "hidden / inter must be multiples of 128, hidden <= 1024");
   if (cfg->max_pos < 1 || cfg->max_pos > 512) return report_error(AUR_ERR_UNSUPPORTED, "max_pos must be 1..512");
   if (cfg->layers < 1 || cfg->vocab < 1 || cfg->type_vocab < 1 || cfg->max_tokens < 1 || cfg->max_seqs < 1)
@@ -234,20 +239,22 @@ int aur_encoder_open(const aur_encoder_config* cfg, aur_encoder** out) {
   e->sm_count = prop.multiProcessorCount;
   e->rows_pad = round_up(cfg->max_tokens, 256) + 512;   // + one full key window past the last sequence
   e->cta_group = cfg->reserved == 1 ? 1 : 2;            // reserved = 1 selects the single-CTA GEMM (bring-up)
-  e->bn = (H % 256 == 0 && I % 256 == 0) ? 256 : 128;
+  e->dh = H / cfg->heads;
+  e->hp = cfg->heads * 64;     // head dim 32 is zero-padded to 64: q.k and P.V are unchanged by zero dims
+  e->bn = (H % 256 == 0 && I % 256 == 0 && e->hp % 256 == 0) ? 256 : 128;
   e->layers.resize(cfg->layers);
   int rc = AUR_OK;
   auto A = [&](auto** p, size_t n) { if (rc == AUR_OK) rc = dev_alloc(p, n); };
   A(&e->word, static_cast<size_t>(cfg->vocab) * H); A(&e->pos, static_cast<size_t>(cfg->max_pos) * H);
   A(&e->type, static_cast<size_t>(cfg->type_vocab) * H); A(&e->emb_g, H); A(&e->emb_b, H);
   for (Layer& l : e->layers) {
-    A(&l.wqkv, static_cast<size_t>(3) * H * H); A(&l.wo, static_cast<size_t>(H) * H);
+    A(&l.wqkv, static_cast<size_t>(3) * e->hp * H); A(&l.wo, static_cast<size_t>(H) * e->hp);
     A(&l.wi, static_cast<size_t>(I) * H); A(&l.wo2, static_cast<size_t>(H) * I);
-    A(&l.bqkv, 3 * H); A(&l.bo, H); A(&l.bi, I); A(&l.bo2, H);
+    A(&l.bqkv, 3 * e->hp); A(&l.bo, H); A(&l.bi, I); A(&l.bo2, H);
     A(&l.ln1_g, H); A(&l.ln1_b, H); A(&l.ln2_g, H); A(&l.ln2_b, H);
   }
   const size_t R = e->rows_pad;
-  A(&e->x, R * H); A(&e->y, R * H); A(&e->qkv, R * 3 * H); A(&e->ctx, R * H); A(&e->inter, R * I);
+  A(&e->x, R * H); A(&e->y, R * H); A(&e->qkv, R * 3 * e->hp); A(&e->ctx, R * e->hp); A(&e->inter, R * I);
   A(&e->d_tok, cfg->max_tokens); A(&e->d_pos, cfg->max_tokens); A(&e->d_cu, cfg->max_seqs + 1);
   e->max_items = cfg->max_seqs * 4;
   A(&e->d_items, e->max_items);
@@ -264,14 +271,15 @@ int aur_encoder_open(const aur_encoder_config* cfg, aur_encoder** out) {
     if (cudaEventCreate(&ev) != cudaSuccess) return fail_open(report_error(AUR_ERR_CUDA, "cudaEventCreate failed"));
   // tensor maps: activations are A operands (box 128 rows), weights B operands (box bn rows)
   const int Ri = static_cast<int>(R);
-  if ((rc = make_tmap(&e->tm_x, e->x, H, Ri, 128)) || (rc = make_tmap(&e->tm_ctx, e->ctx, H, Ri, 128)) ||
-      (rc = make_tmap(&e->tm_inter, e->inter, I, Ri, 128)) || (rc = make_tmap(&e->tm_qkv, e->qkv, 3 * H, Ri, 128)) ||
-      (rc = make_tmap(&e->tmo_qkv, e->qkv, 3 * H, Ri, 32)) || (rc = make_tmap(&e->tmo_y, e->y, H, Ri, 32)) ||
+  const int HP = e->hp;
+  if ((rc = make_tmap(&e->tm_x, e->x, H, Ri, 128)) || (rc = make_tmap(&e->tm_ctx, e->ctx, HP, Ri, 128)) ||
+      (rc = make_tmap(&e->tm_inter, e->inter, I, Ri, 128)) || (rc = make_tmap(&e->tm_qkv, e->qkv, 3 * HP, Ri, 128)) ||
+      (rc = make_tmap(&e->tmo_qkv, e->qkv, 3 * HP, Ri, 32)) || (rc = make_tmap(&e->tmo_y, e->y, H, Ri, 32)) ||
       (rc = make_tmap(&e->tmo_inter, e->inter, I, Ri, 32)))
     return fail_open(rc);
   for (Layer& l : e->layers) {
-    if ((rc = make_tmap(&l.tm_wqkv, l.wqkv, H, 3 * H, e->bn / e->cta_group)) ||
-        (rc = make_tmap(&l.tm_wo, l.wo, H, H, e->bn / e->cta_group)) ||
+    if ((rc = make_tmap(&l.tm_wqkv, l.wqkv, H, 3 * HP, e->bn / e->cta_group)) ||
+        (rc = make_tmap(&l.tm_wo, l.wo, HP, H, e->bn / e->cta_group)) ||
         (rc = make_tmap(&l.tm_wi, l.wi, H, I, e->bn / e->cta_group)) ||
         (rc = make_tmap(&l.tm_wo2, l.wo2, I, H, e->bn / e->cta_group)))
       return fail_open(rc);
@@ -299,17 +307,37 @@ int aur_encoder_load(aur_encoder* e, const char* name, const float* data, int64_
   if (!find_param(e, name, &slot)) return report_error(AUR_ERR_INVALID, "unknown parameter '%s'", name);
   if (slot.count != count) return report_error(AUR_ERR_INVALID, "parameter '%s' has %lld elements, expected %lld", name,
                                                static_cast<long long>(count), static_cast<long long>(slot.count));
+  std::vector<float> padded;
+  int64_t n_up = count;
+  if (slot.pad) {   // head dim 32: spread each head's 32 rows / columns over a 64-wide slot, zeros between
+    const int64_t H = e->cfg.hidden, HP = e->hp, nh = e->cfg.heads, dh = e->dh;
+    if (slot.pad == 1) {
+      const int64_t inner = slot.bf16 ? H : 1;          // wqkv rows have H columns; bqkv is a vector
+      padded.assign(static_cast<size_t>(3 * HP * inner), 0.f);
+      for (int64_t part = 0; part < 3; ++part)
+        for (int64_t h = 0; h < nh; ++h)
+          for (int64_t d = 0; d < dh; ++d)
+            memcpy(&padded[((part * nh + h) * 64 + d) * inner], &data[((part * nh + h) * dh + d) * inner], sizeof(float) * inner);
+    } else {
+      padded.assign(static_cast<size_t>(H * HP), 0.f);
+      for (int64_t r = 0; r < H; ++r)
+        for (int64_t h = 0; h < nh; ++h)
+          memcpy(&padded[r * HP + h * 64], &data[r * H + h * dh], sizeof(float) * dh);
+    }
+    data = padded.data();
+    n_up = static_cast<int64_t>(padded.size());
+  }
   if (slot.bf16) {
-    if (e->stage_elems < static_cast<size_t>(count)) {
+    if (e->stage_elems < static_cast<size_t>(n_up)) {
       if (e->d_stage) cudaFree(e->d_stage);
       e->d_stage = nullptr; e->stage_elems = 0;
-      ENC_TRY(cudaMalloc(reinterpret_cast<void**>(&e->d_stage), sizeof(float) * count));
-      e->stage_elems = count;
+      ENC_TRY(cudaMalloc(reinterpret_cast<void**>(&e->d_stage), sizeof(float) * n_up));
+      e->stage_elems = n_up;
     }
-    ENC_TRY(cudaMemcpyAsync(e->d_stage, data, sizeof(float) * count, cudaMemcpyHostToDevice, e->stream));
-    ENC_TRY(launch_f32_to_bf16(e->d_stage, static_cast<__nv_bfloat16*>(slot.dst), count, e->stream));
+    ENC_TRY(cudaMemcpyAsync(e->d_stage, data, sizeof(float) * n_up, cudaMemcpyHostToDevice, e->stream));
+    ENC_TRY(launch_f32_to_bf16(e->d_stage, static_cast<__nv_bfloat16*>(slot.dst), n_up, e->stream));
   } else {
-    ENC_TRY(cudaMemcpyAsync(slot.dst, data, sizeof(float) * count, cudaMemcpyHostToDevice, e->stream));
+    ENC_TRY(cudaMemcpyAsync(slot.dst, data, sizeof(float) * n_up, cudaMemcpyHostToDevice, e->stream));
   }
   ENC_TRY(cudaStreamSynchronize(e->stream));
   for (size_t i = 0; i < e->missing.size(); ++i)

@@ -41,7 +41,7 @@ class EncoderConfig:
 
 
 BGE_BASE = EncoderConfig()
-MINILM_L6 = EncoderConfig(hidden=384, layers=6, heads=12, inter=1536, pool="mean")   # head dim 32: not yet served by attn_tc.cu
+MINILM_L6 = EncoderConfig(hidden=384, layers=6, heads=12, inter=1536, pool="mean")   # head dim 32, zero-padded to 64 on the device
 BGE_LARGE = EncoderConfig(hidden=1024, layers=24, heads=16, inter=4096)
 
 

@@ -159,7 +159,7 @@ typedef enum aur_pool { AUR_POOL_CLS = 0, AUR_POOL_MEAN = 1 } aur_pool;
 
 typedef struct aur_encoder_config {
   int32_t device;
-  int32_t hidden, layers, heads, inter;   /* head dim (hidden / heads) must be 64         */
+  int32_t hidden, layers, heads, inter;   /* head dim (hidden / heads) 64, or 32 (zero-padded) */
   int32_t vocab, max_pos, type_vocab;     /* max_pos <= 512                               */
   int32_t pool;                           /* aur_pool                                     */
   int32_t normalize;                      /* != 0: L2-normalise the pooled vector         */

@@ -127,6 +127,26 @@ def test_bge_base_matches_hf_golden():
     _check_pooled(got, np.asarray(case["pooled"]))
 
 
+def test_minilm_l6_matches_hf_golden():
+    """all-MiniLM-L6-v2 architecture (H384 / 12 heads = head dim 32, masked-mean pooling; the model the
+    reference deploys, docker-compose.yaml:528), random-init, against transformers.BertModel."""
+    with open(os.path.join(os.path.dirname(__file__), "golden", "bert_ref.json")) as f:
+        case = next(c for c in json.load(f)["cases"] if c["name"] == "minilm_l6")
+    cfg_o = B.BertConfig(**case["cfg"])
+    assert cfg_o.hidden // cfg_o.heads == 32
+    w = B.init_weights(cfg_o, seed=7, bf16=True)
+    with Encoder(_mirror(cfg_o), max_tokens=4096, max_seqs=8) as enc:
+        enc.load_weights(w)
+        got = enc.encode_packed(np.asarray(case["tokens"], np.int32), np.asarray(case["cu_seqlens"], np.int32))
+    _check_pooled(got, np.asarray(case["pooled"]))
+    # and a longer ragged batch against the oracle
+    tok, cu = B.synth_batch(cfg_o, 7, 33, mean_len=180, std_len=150, min_len=1, max_len=512)
+    with Encoder(_mirror(cfg_o), max_tokens=4096, max_seqs=8) as enc:
+        enc.load_weights(w)
+        got = enc.encode_packed(tok, cu)
+    _check_pooled(got, B.encode(cfg_o, w, tok, cu, dtype=np.float32).astype(np.float64))
+
+
 def test_batch_invariance_and_split_calls():
     """A sequence's vector does not depend on what else is in the batch (packed, no padding)."""
     cfg_o = SMALL
@@ -187,7 +207,7 @@ def test_encoder_error_paths():
             enc.encode_packed(np.ones(2, np.int32), np.array([0, 0, 2], np.int32))      # empty sequence
         assert enc.encode_packed(tok, cu).shape == (1, cfg_o.hidden)   # still usable afterwards
     with pytest.raises(N.AuroraError) as e:
-        Encoder(EncoderConfig(hidden=384, layers=1, heads=12, inter=1536))              # head dim 32
+        Encoder(EncoderConfig(hidden=256, layers=1, heads=16, inter=512))               # head dim 16
     assert e.value.code == N.AUR_ERR_UNSUPPORTED
 
 
