@@ -131,6 +131,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  grid_dep_launch();
+  grid_dep_wait();     // the qkv projections come from the previous kernel
 
   uint32_t blk_phase = 0;   // bit j: parity of the next completion of the per-block barriers j
   int it = 0;
@@ -322,8 +324,8 @@ cudaError_t attn_tc_launch(int sm_count, const void* tmap_qkv, const AttnParams&
     attr_set = true;
   }
   const int grid = total < sm_count ? total : sm_count;
-  attn_tc_kernel<<<grid, kAttnThreads, kAttnSmem, s>>>(*reinterpret_cast<const CUtensorMap*>(tmap_qkv), p);
-  return cudaGetLastError();
+  return launch_pdl(attn_tc_kernel, dim3(grid), dim3(kAttnThreads), kAttnSmem, s, 1,
+                    *reinterpret_cast<const CUtensorMap*>(tmap_qkv), p);
 }
 
 }  // namespace aur

@@ -511,7 +511,21 @@ int aur_merge_topk_dev(int32_t device, const double* in_scores64, const int64_t*
   if (n_shards <= 0 || nq <= 0 || k <= 0 || k > kMaxK || n_shards * k > 2048) return fail(AUR_ERR_INVALID, "bad merge shape");
   if (aur_device_count() == 0) return fail(AUR_ERR_NO_DEVICE, "no CUDA device");
   CU_TRY(cudaSetDevice(device));
-  CU_TRY(launch_merge_topk(in_scores64, in_ids, n_shards, nq, k, out_scores, out_ids, out_scores64,
+  CU_TRY(launch_merge_topk(in_scores64, in_ids, static_cast<size_t>(nq) * k, n_shards, nq, k, out_scores, out_ids,
+                           out_scores64, static_cast<cudaStream_t>(stream)));
+  return AUR_OK;
+}
+
+int aur_merge_topk_packed_dev(int32_t device, const void* packed, int32_t n_shards, int32_t nq, int32_t k,
+                              float* out_scores, int64_t* out_ids, double* out_scores64, void* stream) {
+  if (!packed || !out_scores || !out_ids) return fail(AUR_ERR_INVALID, "null argument");
+  if (n_shards <= 0 || nq <= 0 || k <= 0 || k > kMaxK || n_shards * k > 2048) return fail(AUR_ERR_INVALID, "bad merge shape");
+  if (aur_device_count() == 0) return fail(AUR_ERR_NO_DEVICE, "no CUDA device");
+  CU_TRY(cudaSetDevice(device));
+  const size_t plane = static_cast<size_t>(nq) * k;
+  const double* s64 = static_cast<const double*>(packed);
+  const int64_t* ids = static_cast<const int64_t*>(packed) + plane;
+  CU_TRY(launch_merge_topk(s64, ids, 2 * plane, n_shards, nq, k, out_scores, out_ids, out_scores64,
                            static_cast<cudaStream_t>(stream)));
   return AUR_OK;
 }

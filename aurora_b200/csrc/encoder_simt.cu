@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include "internal.h"
+#include "ptx.cuh"
 
 namespace aur {
 namespace {
@@ -73,6 +74,8 @@ embed_ln_kernel(const int32_t* __restrict__ tok, const int32_t* __restrict__ pos
                 const __nv_bfloat16* __restrict__ type_emb, const float* __restrict__ g, const float* __restrict__ b,
                 float eps, int hidden, __nv_bfloat16* __restrict__ out) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();   // the previous forward may still be reading x
   if (row >= n_rows_pad) return;
   const int chunks = hidden >> 3;
   __nv_bfloat16* orow = out + static_cast<size_t>(row) * hidden;
@@ -101,6 +104,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ g, const float* __restrict__ b,
                  float eps, int n_rows, int hidden, __nv_bfloat16* __restrict__ out) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
   if (row >= n_rows) return;
   const int chunks = hidden >> 3;
   const uint4* irow = reinterpret_cast<const uint4*>(in + static_cast<size_t>(row) * hidden);
@@ -119,6 +124,8 @@ __global__ void __launch_bounds__(512)
 pool_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ cu, int hidden, int pool_mode,
             int normalize, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
   __shared__ float red[16];
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
   const int s = blockIdx.x, lo = cu[s], hi = cu[s + 1];
   const int d = 2 * threadIdx.x;
   float a0 = 0.f, a1 = 0.f;
@@ -160,24 +167,21 @@ cudaError_t launch_embed_ln(const int32_t* tok, const int32_t* pos, int n_tok, i
                             const __nv_bfloat16* word, const __nv_bfloat16* pos_emb, const __nv_bfloat16* type_emb,
                             const float* g, const float* b, float eps, int hidden, __nv_bfloat16* out, cudaStream_t s) {
   if (n_rows_pad <= 0) return cudaSuccess;
-  embed_ln_kernel<<<(n_rows_pad + 7) / 8, 256, 0, s>>>(tok, pos, n_tok, n_rows_pad, word, pos_emb, type_emb, g, b, eps,
-                                                       hidden, out);
-  return cudaGetLastError();
+  return launch_pdl(embed_ln_kernel, dim3((n_rows_pad + 7) / 8), dim3(256), 0, s, 1, tok, pos, n_tok, n_rows_pad, word,
+                    pos_emb, type_emb, g, b, eps, hidden, out);
 }
 
 cudaError_t launch_layernorm(const __nv_bfloat16* in, const float* g, const float* b, float eps, int n_rows, int hidden,
                              __nv_bfloat16* out, cudaStream_t s) {
   if (n_rows <= 0) return cudaSuccess;
-  layernorm_kernel<<<(n_rows + 7) / 8, 256, 0, s>>>(in, g, b, eps, n_rows, hidden, out);
-  return cudaGetLastError();
+  return launch_pdl(layernorm_kernel, dim3((n_rows + 7) / 8), dim3(256), 0, s, 1, in, g, b, eps, n_rows, hidden, out);
 }
 
 cudaError_t launch_pool(const __nv_bfloat16* x, const int32_t* cu, int n_seq, int hidden, int pool_mode, int normalize,
                         float* out_f32, __nv_bfloat16* out_bf16, cudaStream_t s) {
   if (n_seq <= 0) return cudaSuccess;
   const int threads = ((hidden / 2 + 31) / 32) * 32;
-  pool_kernel<<<n_seq, threads, 0, s>>>(x, cu, hidden, pool_mode, normalize, out_f32, out_bf16);
-  return cudaGetLastError();
+  return launch_pdl(pool_kernel, dim3(n_seq), dim3(threads), 0, s, 1, x, cu, hidden, pool_mode, normalize, out_f32, out_bf16);
 }
 
 cudaError_t launch_f32_to_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s) {

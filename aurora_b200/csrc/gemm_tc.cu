@@ -117,6 +117,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if constexpr (G == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  grid_dep_launch();   // the next kernel may take over SMs as this grid's CTAs retire
+  grid_dep_wait();     // everything above overlapped the previous kernel's tail; its output is needed from here on
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (every CTA)
@@ -258,17 +260,9 @@ cudaError_t launch_one(int sm_count, const void* tmap_a, const void* tmap_b, con
     attr_set = true;
   }
   const int tiles = p.m_tiles * p.n_tiles, groups = sm_count / G;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(static_cast<unsigned>((tiles < groups ? tiles : groups) * G));
-  cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = GemmSmem<BN, G>::kTotal;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, *reinterpret_cast<const CUtensorMap*>(tmap_a),
-                            *reinterpret_cast<const CUtensorMap*>(tmap_b), *reinterpret_cast<const CUtensorMap*>(tmap_out), p);
+  return launch_pdl(kern, dim3(static_cast<unsigned>((tiles < groups ? tiles : groups) * G)), dim3(kGemmThreads),
+                    GemmSmem<BN, G>::kTotal, s, G, *reinterpret_cast<const CUtensorMap*>(tmap_a),
+                    *reinterpret_cast<const CUtensorMap*>(tmap_b), *reinterpret_cast<const CUtensorMap*>(tmap_out), p);
 }
 
 }  // namespace

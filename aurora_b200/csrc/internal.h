@@ -103,7 +103,8 @@ struct FinalizeArgs {
   int sort_cap;      // set by launch_finalize: keys the shared sort buffer holds
 };
 cudaError_t launch_finalize(const FinalizeArgs& a, cudaStream_t s);
-cudaError_t launch_merge_topk(const double* in_s, const int64_t* in_ids, int n_shards, int nq, int k,
+// shard_stride: elements between consecutive shards' blocks in in_s / in_ids
+cudaError_t launch_merge_topk(const double* in_s, const int64_t* in_ids, size_t shard_stride, int n_shards, int nq, int k,
                               float* out_s, int64_t* out_ids, double* out_s64, cudaStream_t s);
 cudaError_t launch_cosine_pairs(const float* a, const float* b, int64_t n, int dim, int clamp, double* out,
                                 cudaStream_t s);
@@ -141,6 +142,28 @@ cudaError_t launch_layernorm(const __nv_bfloat16* in, const float* g, const floa
 cudaError_t launch_pool(const __nv_bfloat16* x, const int32_t* cu, int n_seq, int hidden, int pool_mode, int normalize,
                         float* out_f32, __nv_bfloat16* out_bf16, cudaStream_t s);
 cudaError_t launch_f32_to_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s);
+
+// Launch with programmatic dependent launch enabled (and an optional cluster size): the kernel may
+// start its prologue while the previous kernel of the stream drains; it must call
+// ptx::grid_dep_wait() before touching that kernel's output.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster,
+                       Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[n].val.programmaticStreamSerializationAllowed = 1;
+  ++n;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr; cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // Error reporting shared by the translation units behind the C ABI (thread-local message).
 int report_error(int code, const char* fmt, ...);

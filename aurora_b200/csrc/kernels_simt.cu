@@ -290,8 +290,8 @@ finalize_kernel(FinalizeArgs a) {
 
 // Cross-shard merge of exact (fp64 score, id) lists: [n_shards, nq, k] -> [nq, k].
 __global__ void __launch_bounds__(256)
-merge_topk_kernel(const double* __restrict__ in_s, const int64_t* __restrict__ in_ids, int n_shards, int nq, int k,
-                  float* out_s, int64_t* out_ids, double* out_s64) {
+merge_topk_kernel(const double* __restrict__ in_s, const int64_t* __restrict__ in_ids, size_t shard_stride, int n_shards,
+                  int nq, int k, float* out_s, int64_t* out_ids, double* out_s64) {
   extern __shared__ uint8_t sm[];
   double* sc = reinterpret_cast<double*>(sm);
   int64_t* id = reinterpret_cast<int64_t*>(sc + n_shards * k);
@@ -299,7 +299,7 @@ merge_topk_kernel(const double* __restrict__ in_s, const int64_t* __restrict__ i
   const int qi = blockIdx.x, n = n_shards * k;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int sh = i / k, t = i % k;
-    const size_t o = (static_cast<size_t>(sh) * nq + qi) * k + t;
+    const size_t o = static_cast<size_t>(sh) * shard_stride + static_cast<size_t>(qi) * k + t;
     sc[i] = in_s[o]; id[i] = in_ids[o];
   }
   if (threadIdx.x == 0) s_nvalid = 0;
@@ -420,11 +420,11 @@ cudaError_t launch_finalize(const FinalizeArgs& a_in, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_merge_topk(const double* in_s, const int64_t* in_ids, int n_shards, int nq, int k, float* out_s,
-                              int64_t* out_ids, double* out_s64, cudaStream_t s) {
+cudaError_t launch_merge_topk(const double* in_s, const int64_t* in_ids, size_t shard_stride, int n_shards, int nq, int k,
+                              float* out_s, int64_t* out_ids, double* out_s64, cudaStream_t s) {
   const size_t smem = static_cast<size_t>(n_shards) * k * 16;
   if (smem > 48 * 1024) return cudaErrorInvalidValue;
-  merge_topk_kernel<<<nq, 256, smem, s>>>(in_s, in_ids, n_shards, nq, k, out_s, out_ids, out_s64);
+  merge_topk_kernel<<<nq, 256, smem, s>>>(in_s, in_ids, shard_stride, n_shards, nq, k, out_s, out_ids, out_s64);
   return cudaGetLastError();
 }
 

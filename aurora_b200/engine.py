@@ -129,6 +129,15 @@ class Index:
         return {f: getattr(st, f) for f, _ in N.AurStats._fields_}
 
 
+def merge_topk_packed_dev(device: int, packed_ptr: int, n_shards: int, nq: int, k: int, out_scores_ptr: int,
+                          out_ids_ptr: int, out_scores64_ptr: int = 0, stream: int = 0) -> None:
+    """packed: [n_shards][2][nq][k] 8-byte words (plane 0 fp64 scores, plane 1 int64 ids)."""
+    lib = N.load()
+    N.check(lib.aur_merge_topk_packed_dev(int(device), C.c_void_p(packed_ptr), int(n_shards), int(nq), int(k),
+                                          C.c_void_p(out_scores_ptr), C.c_void_p(out_ids_ptr),
+                                          C.c_void_p(out_scores64_ptr), C.c_void_p(stream)))
+
+
 def merge_topk_dev(device: int, in_scores64_ptr: int, in_ids_ptr: int, n_shards: int, nq: int, k: int,
                    out_scores_ptr: int, out_ids_ptr: int, out_scores64_ptr: int = 0, stream: int = 0) -> None:
     lib = N.load()

@@ -40,12 +40,14 @@ class ShardedSearcher:
         s64, ids = self.local_search(queries, k)
         if self.world == 1:
             return self.merge(s64.unsqueeze(0), ids.unsqueeze(0), k)
-        nq = s64.shape[0]                       # gathered along dim 0 (the layout both backends accept)
-        all_s = torch.empty((self.world * nq, k), dtype=s64.dtype, device=s64.device)
-        all_i = torch.empty((self.world * nq, k), dtype=ids.dtype, device=ids.device)
-        self.dist.all_gather_into_tensor(all_s, s64.contiguous())
-        self.dist.all_gather_into_tensor(all_i, ids.contiguous())
-        return self.merge(all_s.view(self.world, nq, k), all_i.view(self.world, nq, k), k)
+        nq = s64.shape[0]
+        # ONE all-gather: fp64 keys and int64 ids travel as the two planes of an 8-byte-word buffer
+        # (gathered along dim 0, the layout both backends accept)
+        pack = torch.stack((s64.contiguous().view(torch.int64), ids.contiguous()), dim=0).view(2 * nq, k)
+        allp = torch.empty((self.world * 2 * nq, k), dtype=torch.int64, device=ids.device)
+        self.dist.all_gather_into_tensor(allp, pack)
+        allp = allp.view(self.world, 2, nq, k)
+        return self.merge(allp[:, 0].contiguous().view(torch.float64), allp[:, 1].contiguous(), k)
 
 
 def make_gpu_searcher(index, dist=None, world: int = 1, device: int = 0, stream: Optional[int] = None) -> ShardedSearcher:

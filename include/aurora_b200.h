@@ -130,6 +130,13 @@ int aur_merge_topk_dev(int32_t device, const double* in_scores64, const int64_t*
                        float* out_scores, int64_t* out_ids, double* out_scores64,
                        void* stream);
 
+/* Same merge over ONE gathered buffer: each shard contributes a block of 2*nq*k 8-byte words, plane 0
+ * its fp64 scores [nq,k], plane 1 its int64 ids [nq,k] (pass scores64_dev = block, ids_dev = block +
+ * nq*k to aur_search_dev), so the exchange is a single all-gather.  packed: [n_shards][2][nq][k]. */
+int aur_merge_topk_packed_dev(int32_t device, const void* packed, int32_t n_shards, int32_t nq,
+                              int32_t k, float* out_scores, int64_t* out_ids,
+                              double* out_scores64, void* stream);
+
 /* Pairwise cosine of row i of a with row i of b (host buffers, fp32 in, fp64 out).
  * Replaces SimilarityStrategy._cosine_similarity
  * (server/services/correlation/strategies/similarity.py:84-98); clamp != 0 applies its

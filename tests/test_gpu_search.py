@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from aurora_b200 import _native as N
-from aurora_b200.engine import DeviceBuffer, Index, cosine_pairs, merge_topk_dev, to_bf16_bits
+from aurora_b200.engine import DeviceBuffer, Index, cosine_pairs, merge_topk_dev, merge_topk_packed_dev, to_bf16_bits
 from oracle import cosine_topk as O
 
 pytestmark = pytest.mark.gpu
@@ -197,6 +197,15 @@ def test_two_shards_merge_equals_single_index():
     ids = doi.download(np.empty((nq, k), np.int64))
     sc = dos.download(np.empty((nq, k), np.float32))
     _check(ids, sc, full_ids, full_sc)
+    # the packed layout used by the single all-gather: [shard][plane 0 = fp64 keys | plane 1 = ids]
+    packed = np.empty((G, 2, nq, k), np.int64)
+    packed[:, 0] = s64.view(np.int64)
+    packed[:, 1] = sid
+    dpk = DeviceBuffer(packed.nbytes).upload(packed)
+    dos2, doi2 = DeviceBuffer(nq * k * 4), DeviceBuffer(nq * k * 8)
+    merge_topk_packed_dev(0, dpk.ptr, G, nq, k, dos2.ptr, doi2.ptr)
+    assert np.array_equal(doi2.download(np.empty((nq, k), np.int64)), ids)
+    assert np.array_equal(dos2.download(np.empty((nq, k), np.float32)), sc)
 
 
 # ------------------------------------------------------------------ in-repo cosine (a7)
