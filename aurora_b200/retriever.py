@@ -30,7 +30,7 @@ import threading
 import uuid
 from datetime import datetime, timezone
 from types import SimpleNamespace
-from typing import Any, Callable, Dict, List, Optional
+from typing import Any, Callable, Dict, List, Optional, Tuple
 
 import numpy as np
 
@@ -73,6 +73,9 @@ class KnowledgeBase:
             def index_factory(dim, cap):
                 return Index(dim, cap, dtype="bf16", device=device)
         self.index = index_factory(self.dim, int(capacity))
+        from .bm25 import BM25Index
+
+        self.sparse = BM25Index()       # keyword leg of the hybrid query (host text work, like in Weaviate)
         self._lock = threading.RLock()  # the reference's module globals are unlocked (weaviate_client.py:31-32)
         self._props: Dict[int, Dict[str, Any]] = {}   # id -> properties
         self._key2id: Dict[str, int] = {}             # uuid5 -> id
@@ -130,37 +133,65 @@ class KnowledgeBase:
                 self.index.add(vecs, ids, ucode, ocode)
             for i, (_, props) in enumerate(metas):
                 self._props[int(ids[i])] = props
+                self.sparse.add(int(ids[i]), texts[i])
         return len(metas)
 
     # ------------------------------------------------------------------ search
     def query(self, query: str, limit: int, filters=None, user_id: Optional[str] = None,
-              org_id: Optional[str] = None) -> List[SimpleNamespace]:
-        """Dense top-``limit``.  Tenant scope (user OR org) runs inside the kernel; any extra
-        ``filters`` expression is applied to the metadata of an over-fetched result."""
+              org_id: Optional[str] = None, alpha: Optional[float] = None) -> List[SimpleNamespace]:
+        """Top-``limit`` objects.  ``alpha`` None or >= 1: pure vector search, ``score`` = cosine
+        (near_text, incident_feedback/weaviate_client.py:286-297).  ``alpha`` < 1: hybrid with ranked
+        fusion (weaviate_client.py:252-259): dense and BM25 lists fused as alpha/(rank+60) +
+        (1-alpha)/(rank+60), ``score`` = the fused score.  Tenant scope (user OR org) runs inside the
+        kernel for the dense leg and as a pre-filter for the keyword leg; any extra ``filters``
+        expression is applied to the metadata of the over-fetched lists."""
         if limit <= 0:
             return []
-        qv = self.encoder.encode([query])
+        hybrid = alpha is not None and alpha < 1.0
+        dense_w = 1.0 if not hybrid else max(0.0, float(alpha))
+        qv = self.encoder.encode([query]) if dense_w > 0.0 else None
         with self._lock:
-            q_user = q_org = None
-            if user_id is not None or org_id is not None:
-                q_user = np.array([self._code(self._user_code, user_id, False) if user_id else -2], dtype=np.int32)
-                q_org = np.array([self._code(self._org_code, org_id, False) if org_id else -1], dtype=np.int32)
-                if q_org[0] == -2:
-                    q_org[0] = -1
-            fetch = limit if filters is None else _MAX_FETCH
-            fetch = max(1, min(_MAX_FETCH, fetch))
-            ids, scores = self.index.search(qv, fetch, q_user, q_org)
+            def ok(props) -> bool:
+                return props is not None and (filters is None or filters.matches(props))
+
+            dense: List[Tuple[int, float]] = []
+            if qv is not None:
+                q_user = q_org = None
+                if user_id is not None or org_id is not None:
+                    q_user = np.array([self._code(self._user_code, user_id, False) if user_id else -2], dtype=np.int32)
+                    q_org = np.array([self._code(self._org_code, org_id, False) if org_id else -1], dtype=np.int32)
+                    if q_org[0] == -2:
+                        q_org[0] = -1
+                fetch = limit if (filters is None and not hybrid) else _MAX_FETCH
+                fetch = max(1, min(_MAX_FETCH, fetch))
+                ids, scores = self.index.search(qv, fetch, q_user, q_org)
+                for rid, sc in zip(ids[0], scores[0]):
+                    if rid < 0:
+                        break
+                    if ok(self._props.get(int(rid))):
+                        dense.append((int(rid), float(sc)))
+            if not hybrid:
+                picked = [(rid, sc, sc) for rid, sc in dense[:limit]]
+            else:
+                def allow(doc: int) -> bool:
+                    props = self._props.get(doc)
+                    if not ok(props):
+                        return False
+                    if user_id is None and org_id is None:
+                        return True
+                    return (user_id is not None and props.get("user_id") == user_id) or \
+                           (bool(org_id) and props.get("org_id") == org_id)
+
+                sparse = self.sparse.search(query, _MAX_FETCH, allow)
+                from .bm25 import ranked_fusion
+
+                cos = dict(dense)
+                fused = ranked_fusion([(dense_w, [d for d, _ in dense]), (1.0 - dense_w, [d for d, _ in sparse])], limit)
+                picked = [(rid, fs, cos.get(rid)) for rid, fs in fused]
             out = []
-            for rid, sc in zip(ids[0], scores[0]):
-                if rid < 0:
-                    break
-                props = self._props.get(int(rid))
-                if props is None or (filters is not None and not filters.matches(props)):
-                    continue
-                out.append(SimpleNamespace(properties=dict(props), uuid=None,
-                                           metadata=SimpleNamespace(score=float(sc), distance=1.0 - float(sc))))
-                if len(out) == limit:
-                    break
+            for rid, score, cosine in picked:
+                meta = SimpleNamespace(score=float(score), distance=None if cosine is None else 1.0 - float(cosine))
+                out.append(SimpleNamespace(properties=dict(self._props[rid]), uuid=None, metadata=meta))
             return out
 
     # ------------------------------------------------------------------ deletes / counts
@@ -174,6 +205,7 @@ class KnowledgeBase:
                 self.index.remove(np.array(ids, dtype=np.int64))
                 for rid in ids:
                     p = self._props.pop(rid)
+                    self.sparse.remove(rid)
                     self._key2id.pop(generate_uuid5(f"{p['user_id']}:{p['document_id']}:{p['chunk_index']}"), None)
             return len(ids)
 
@@ -189,7 +221,9 @@ class _QueryFacade:
 
     def hybrid(self, query: str, limit: int = 10, alpha: float = 0.5, fusion_type=None, filters=None,
                return_metadata=None, **_):
-        return SimpleNamespace(objects=self._kb.query(query, limit, filters=filters))
+        if fusion_type not in (None, HybridFusion.RANKED):
+            raise NotImplementedError("only HybridFusion.RANKED (what the reference requests) is implemented")
+        return SimpleNamespace(objects=self._kb.query(query, limit, filters=filters, alpha=alpha))
 
     def near_text(self, query: str, limit: int = 10, filters=None, return_metadata=None, **_):
         return SimpleNamespace(objects=self._kb.query(query, limit, filters=filters))
@@ -271,7 +305,7 @@ def search_knowledge_base(user_id: str, query: str, limit: int = 5, alpha: float
     if not query.strip():
         return []
     try:
-        objs = _get_kb().query(query, limit, user_id=user_id, org_id=org_id)
+        objs = _get_kb().query(query, limit, user_id=user_id, org_id=org_id, alpha=alpha)
         results = []
         for obj in objs:
             score = obj.metadata.score if obj.metadata else 0.0

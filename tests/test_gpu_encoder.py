@@ -244,8 +244,11 @@ def test_retriever_with_cuda_encoder_end_to_end():
         assert R.insert_chunks("u1", "doc1", "runbook.md", chunks, org_id="o1") == 12
         assert R.insert_chunks("u2", "doc2", "other.md", [{"content": "unrelated billing notes", "chunk_index": 0}]) == 1
         assert R.get_document_chunk_count("u1", "doc1") == 12
-        hits = R.search_knowledge_base("u1", "Recovery\nrunbook step 7: restart service alpha-7 and check queue depth", limit=3)
+        q7 = "Recovery\nrunbook step 7: restart service alpha-7 and check queue depth"
+        hits = R.search_knowledge_base("u1", q7, limit=3, alpha=1.0)                  # pure vector: score = cosine
         assert hits and hits[0]["chunk_index"] == 7 and hits[0]["document_id"] == "doc1" and hits[0]["score"] > 0.999
+        hy = R.search_knowledge_base("u1", q7, limit=3)                               # default alpha=0.5: ranked fusion
+        assert hy[0]["chunk_index"] == 7 and hy[0]["score"] == pytest.approx(1.0 / 60.0)
         assert set(hits[0]) == {"content", "heading_context", "source_filename", "document_id", "chunk_index", "score"}
         assert all(h["document_id"] == "doc1" for h in R.search_knowledge_base("u1", "billing", limit=5))   # tenant scope
         assert R.search_knowledge_base("u1", "   ") == []

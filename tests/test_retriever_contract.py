@@ -48,7 +48,10 @@ def test_insert_search_roundtrip_and_result_shape(kb):
     assert res[0]["content"].startswith("restart the payment service")
     assert res[0]["source_filename"] == "runbook.md" and res[0]["document_id"] == "doc-a"
     assert res[0]["score"] >= res[1]["score"]
-    assert -1.0 <= res[0]["score"] <= 1.0 + 1e-6
+    # alpha=0.5 (default): hybrid ranked fusion, top of both lists -> 0.5/60 + 0.5/60 (:252-259)
+    assert res[0]["score"] == pytest.approx(1.0 / 60.0)
+    pure = kb.search_knowledge_base("u1", "payment service latency", limit=2, alpha=1.0)
+    assert pure[0]["content"] == res[0]["content"] and -1.0 <= pure[0]["score"] <= 1.0 + 1e-6   # cosine
 
 
 def test_blank_query_and_empty_chunks(kb):
@@ -71,8 +74,49 @@ def test_min_score_only_filters_when_positive(kb):
     kb.insert_chunks("u", "d", "f.md", _chunks("cpu saturation on api gateway", "completely unrelated gardening tips"))
     all_ = kb.search_knowledge_base("u", "api gateway cpu", limit=5, min_score=0.0)
     assert len(all_) == 2
-    some = kb.search_knowledge_base("u", "api gateway cpu", limit=5, min_score=0.5)   # :266
+    some = kb.search_knowledge_base("u", "api gateway cpu", limit=5, alpha=1.0, min_score=0.5)   # :266, cosine scores
     assert [r["content"] for r in some] == ["cpu saturation on api gateway"]
+    # hybrid scores are rank-fusion values <= 1/60: the same threshold removes everything, as in the reference
+    assert kb.search_knowledge_base("u", "api gateway cpu", limit=5, min_score=0.5) == []
+    top = kb.search_knowledge_base("u", "api gateway cpu", limit=5, min_score=0.0166)
+    assert [r["content"] for r in top] == ["cpu saturation on api gateway"]
+
+
+def test_hybrid_keyword_leg_and_alpha(kb):
+    """BM25 leg + ranked fusion (weaviate_client.py:252-259): an exact rare keyword wins the sparse list."""
+    kb.insert_chunks("u", "d", "f.md", _chunks("generic notes about restarting services and checking dashboards",
+                                               "error code zx9981 means the ledger shard is read only",
+                                               "more generic notes about services dashboards and restarts"))
+    kw = kb.search_knowledge_base("u", "zx9981", limit=3, alpha=0.0)              # keyword only
+    assert [r["chunk_index"] for r in kw] == [1] and kw[0]["score"] == pytest.approx(1.0 / 60.0)
+    hy = kb.search_knowledge_base("u", "zx9981", limit=3, alpha=0.5)
+    assert hy[0]["chunk_index"] == 1 and len(hy) == 3                             # dense leg still contributes the rest
+    assert hy[0]["score"] > hy[1]["score"] >= hy[2]["score"] > 0
+    # tenant scope applies to the keyword leg too
+    kb.insert_chunks("someone-else", "d9", "x.md", _chunks("zx9981 zx9981 zx9981"))
+    assert {r["document_id"] for r in kb.search_knowledge_base("u", "zx9981", limit=5, alpha=0.0)} == {"d"}
+    # deleting a document removes its postings
+    kb.delete_document_chunks("u", "d")
+    assert kb.search_knowledge_base("u", "zx9981", limit=5, alpha=0.0) == []
+
+
+def test_bm25_and_ranked_fusion_units():
+    from aurora_b200.bm25 import BM25Index, ranked_fusion, tokenize
+
+    assert tokenize("Kafka-consumer LAG, alert#7!") == ["kafka", "consumer", "lag", "alert", "7"]
+    ix = BM25Index()
+    ix.add(1, "redis cache eviction policy")
+    ix.add(2, "redis redis redis cluster failover")
+    ix.add(3, "postgres vacuum tuning")
+    top = ix.search("redis failover", 10)
+    assert [d for d, _ in top] == [2, 1]                                           # more matches, rarer term
+    assert ix.search("redis", 10, allow=lambda d: d != 2)[0][0] == 1
+    ix.add(1, "now about kafka")                                                   # upsert replaces postings
+    assert [d for d, _ in ix.search("redis", 10)] == [2]
+    assert ix.remove(2) and not ix.remove(2) and ix.search("redis", 10) == []
+    fused = ranked_fusion([(0.5, [10, 11, 12]), (0.5, [12, 10])], 3)
+    assert [d for d, _ in fused] == [10, 12, 11]
+    assert fused[0][1] == pytest.approx(0.5 / 60 + 0.5 / 61) and fused[1][1] == pytest.approx(0.5 / 62 + 0.5 / 60)
 
 
 def test_upsert_is_idempotent_on_user_doc_chunk(kb):
