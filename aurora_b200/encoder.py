@@ -229,3 +229,58 @@ def get_embedding_client() -> EmbeddingClient:                 # embedding_clien
     if _factory is None:
         raise RuntimeError("call aurora_b200.encoder.configure_embedding_client(factory) first")
     return _factory()
+
+
+# ----------------------------------------------------------------------------- checkpoint loading
+def read_safetensors(path: str) -> Dict[str, np.ndarray]:
+    """Minimal safetensors reader (8-byte little-endian header length, JSON header, raw tensors):
+    F32 / F16 / BF16 tensors come back as float32 arrays.  No third-party dependency."""
+    import json
+    import struct
+
+    out: Dict[str, np.ndarray] = {}
+    with open(path, "rb") as f:
+        (hlen,) = struct.unpack("<Q", f.read(8))
+        header = json.loads(f.read(hlen))
+        base = 8 + hlen
+        for name, info in header.items():
+            if name == "__metadata__":
+                continue
+            lo, hi = info["data_offsets"]
+            f.seek(base + lo)
+            raw = f.read(hi - lo)
+            dt = info["dtype"]
+            if dt == "F32":
+                a = np.frombuffer(raw, dtype=np.float32)
+            elif dt == "F16":
+                a = np.frombuffer(raw, dtype=np.float16).astype(np.float32)
+            elif dt == "BF16":
+                a = (np.frombuffer(raw, dtype=np.uint16).astype(np.uint32) << np.uint32(16)).view(np.float32)
+            else:
+                continue                                   # integer buffers (position_ids) are not parameters
+            out[name] = a.reshape(info["shape"]).copy()
+    return out
+
+
+def from_hf_bert(state: Dict[str, np.ndarray], cfg: EncoderConfig) -> Dict[str, np.ndarray]:
+    """HuggingFace BertModel parameter names (with or without a ``bert.`` prefix) -> the names
+    ``aur_encoder_load`` expects; query / key / value matrices are stacked into ``wqkv``."""
+    def g(name: str) -> np.ndarray:
+        for prefix in ("", "bert."):
+            if prefix + name in state:
+                return np.asarray(state[prefix + name], dtype=np.float32)
+        raise KeyError(name)
+
+    w = {"word_emb": g("embeddings.word_embeddings.weight"), "pos_emb": g("embeddings.position_embeddings.weight"),
+         "type_emb": g("embeddings.token_type_embeddings.weight"), "emb_ln_g": g("embeddings.LayerNorm.weight"),
+         "emb_ln_b": g("embeddings.LayerNorm.bias")}
+    for l in range(cfg.layers):
+        p, q = f"l{l}.", f"encoder.layer.{l}."
+        w[p + "wqkv"] = np.concatenate([g(q + f"attention.self.{n}.weight") for n in ("query", "key", "value")], axis=0)
+        w[p + "bqkv"] = np.concatenate([g(q + f"attention.self.{n}.bias") for n in ("query", "key", "value")], axis=0)
+        w[p + "wo"], w[p + "bo"] = g(q + "attention.output.dense.weight"), g(q + "attention.output.dense.bias")
+        w[p + "ln1_g"], w[p + "ln1_b"] = g(q + "attention.output.LayerNorm.weight"), g(q + "attention.output.LayerNorm.bias")
+        w[p + "wi"], w[p + "bi"] = g(q + "intermediate.dense.weight"), g(q + "intermediate.dense.bias")
+        w[p + "wo2"], w[p + "bo2"] = g(q + "output.dense.weight"), g(q + "output.dense.bias")
+        w[p + "ln2_g"], w[p + "ln2_b"] = g(q + "output.LayerNorm.weight"), g(q + "output.LayerNorm.bias")
+    return w
