@@ -21,7 +21,7 @@ KERNEL_NAMES = {0: "auto", 1: "simt", 2: "tcgen05-cta1", 3: "tcgen05-cta2"}
 # every symbol include/aurora_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "aur_abi_version", "aur_last_error", "aur_device_count", "aur_open", "aur_close", "aur_get_stats",
-    "aur_set_option", "aur_sync", "aur_add", "aur_add_dev", "aur_remove", "aur_search", "aur_search_dev",
+    "aur_set_option", "aur_sync", "aur_add", "aur_add_dev", "aur_export", "aur_remove", "aur_search", "aur_search_dev",
     "aur_merge_topk_dev", "aur_merge_topk_packed_dev", "aur_cosine_pairs", "aur_dev_malloc", "aur_dev_free", "aur_memcpy_h2d", "aur_memcpy_d2h",
     "aur_debug_tc_scores",
     "aur_encoder_open", "aur_encoder_close", "aur_encoder_load", "aur_encode", "aur_encode_append",
@@ -87,6 +87,7 @@ def load():
         "aur_sync": (C.c_int, [vp]),
         "aur_add": (C.c_int, [vp, vp, vp, vp, vp, i64]),
         "aur_add_dev": (C.c_int, [vp, vp, vp, vp, vp, i64, vp]),
+        "aur_export": (C.c_int, [vp, vp, vp, vp, vp, vp, i64]),
         "aur_remove": (C.c_int, [vp, vp, i64, C.POINTER(i64)]),
         "aur_search": (C.c_int, [vp, vp, i32, i32, vp, vp, vp, vp]),
         "aur_search_dev": (C.c_int, [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]),

@@ -403,6 +403,24 @@ int aur_get_stats(aur_index* ix, aur_stats* out) {
   return AUR_OK;
 }
 
+int aur_export(aur_index* ix, void* rows_out, int64_t* ids_out, int32_t* user_out, int32_t* org_out, uint8_t* live_out,
+               int64_t n) {
+  if (!ix || !rows_out || !ids_out || !live_out) return fail(AUR_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  if (n != ix->rows) return fail(AUR_ERR_INVALID, "n must equal aur_stats.rows (%lld)", (long long)ix->rows);
+  if (n == 0) return AUR_OK;
+  CU_TRY(cudaSetDevice(ix->device));
+  CU_TRY(cudaStreamSynchronize(ix->stream));
+  std::vector<float> inv(static_cast<size_t>(n));
+  CU_TRY(cudaMemcpy(inv.data(), ix->d_inv_norm, sizeof(float) * n, cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(rows_out, ix->d_rows, static_cast<size_t>(n) * ix->dim * ix->elt, cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(ids_out, ix->d_ids, sizeof(int64_t) * n, cudaMemcpyDeviceToHost));
+  if (user_out) CU_TRY(cudaMemcpy(user_out, ix->d_user, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+  if (org_out) CU_TRY(cudaMemcpy(org_out, ix->d_org, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < n; ++i) live_out[i] = inv[static_cast<size_t>(i)] == inv[static_cast<size_t>(i)];   // NaN = tombstone
+  return AUR_OK;
+}
+
 int aur_set_option(aur_index* ix, const char* key, int64_t value) {
   if (!ix || !key) return fail(AUR_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> lk(ix->mu);

@@ -90,6 +90,33 @@ class Index:
         N.check(self._lib.aur_remove(self._h, _ptr(ids), ids.shape[0], C.byref(removed)))
         return int(removed.value)
 
+    # -------------------------------------------------------------- snapshot
+    def export(self):
+        """All appended rows in append order: (rows [n, dim] uint16 bf16 bits or float32, ids, user codes,
+        org codes, live mask).  Tombstoned rows are included with live = False."""
+        n = self.stats()["rows"]
+        rows = np.empty((n, self.dim), dtype=np.uint16 if self.dtype == N.AUR_BF16 else np.float32)
+        ids = np.empty(n, dtype=np.int64)
+        user, org = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32)
+        live = np.empty(n, dtype=np.uint8)
+        N.check(self._lib.aur_export(self._h, _ptr(rows), _ptr(ids), _ptr(user), _ptr(org), _ptr(live), n))
+        return rows, ids, user, org, live.astype(bool)
+
+    def save(self, path: str) -> None:
+        """Snapshot of the live rows (tombstones are compacted away) as one .npz file."""
+        rows, ids, user, org, live = self.export()
+        np.savez(path, rows=rows[live], ids=ids[live], user=user[live], org=org[live], dim=self.dim,
+                 dtype=self.dtype, capacity=self.capacity)
+
+    @classmethod
+    def load(cls, path: str, capacity: Optional[int] = None, device: int = 0) -> "Index":
+        z = np.load(path if path.endswith(".npz") else path + ".npz")
+        dtype = "bf16" if int(z["dtype"]) == N.AUR_BF16 else "f32"
+        ix = cls(int(z["dim"]), int(capacity or z["capacity"]), dtype=dtype, device=device)
+        if len(z["ids"]):
+            ix.add(z["rows"], z["ids"], z["user"], z["org"])
+        return ix
+
     # -------------------------------------------------------------- search
     def search(self, queries: np.ndarray, k: int, q_user: Optional[np.ndarray] = None,
                q_org: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:

@@ -194,6 +194,50 @@ class KnowledgeBase:
                 out.append(SimpleNamespace(properties=dict(self._props[rid]), uuid=None, metadata=meta))
             return out
 
+    # ------------------------------------------------------------------ persistence
+    def save(self, directory: str) -> None:
+        """Durable snapshot (replaces the Weaviate data volume, docker-compose.yaml:477-478): the live
+        vectors as ``shard.npz`` (tombstones compacted away) and the chunk metadata as ``meta.json``."""
+        import json
+
+        os.makedirs(directory, exist_ok=True)
+        with self._lock:
+            self.index.save(os.path.join(directory, "shard"))
+            meta = {"version": 1, "dim": self.dim, "next_id": self._next_id, "user_code": self._user_code,
+                    "org_code": self._org_code, "key2id": self._key2id,
+                    "props": {str(k): v for k, v in self._props.items()}}
+            tmp = os.path.join(directory, "meta.json.tmp")
+            with open(tmp, "w", encoding="utf-8") as f:
+                json.dump(meta, f)
+            os.replace(tmp, os.path.join(directory, "meta.json"))
+
+    @classmethod
+    def load(cls, directory: str, encoder, capacity: int = 1 << 20, device: int = 0, index_loader=None) -> "KnowledgeBase":
+        """Rebuild from ``save``: vectors go back into HBM as they were stored (no re-encoding), the
+        keyword index is rebuilt from the chunk texts."""
+        import json
+
+        with open(os.path.join(directory, "meta.json"), encoding="utf-8") as f:
+            meta = json.load(f)
+        if int(meta["dim"]) != int(encoder.dim):
+            raise ValueError(f"snapshot is {meta['dim']}-d, encoder is {encoder.dim}-d")
+        if index_loader is None:
+            from .engine import Index
+
+            def index_loader(path, cap):
+                return Index.load(path, capacity=cap, device=device)
+        loaded = index_loader(os.path.join(directory, "shard"), int(capacity))
+        kb = cls(encoder, capacity=capacity, device=device, index_factory=lambda dim, cap: loaded)
+        kb._next_id = int(meta["next_id"])
+        kb._user_code = {k: int(v) for k, v in meta["user_code"].items()}
+        kb._org_code = {k: int(v) for k, v in meta["org_code"].items()}
+        kb._key2id = {k: int(v) for k, v in meta["key2id"].items()}
+        kb._props = {int(k): v for k, v in meta["props"].items()}
+        for rid, p in kb._props.items():
+            heading = p.get("heading_context", "")
+            kb.sparse.add(rid, (heading + "\n" if heading else "") + p.get("content", ""))
+        return kb
+
     # ------------------------------------------------------------------ deletes / counts
     def _matching_ids(self, pred) -> List[int]:
         return [rid for rid, p in self._props.items() if pred(p)]

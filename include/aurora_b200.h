@@ -102,6 +102,13 @@ int aur_add_dev(aur_index* ix, const void* rows_dev, const int64_t* ids_host,
                 const int32_t* user_codes_host, const int32_t* org_codes_host,
                 int64_t n, void* stream);
 
+/* Snapshot.  Replaces the Weaviate data volume (docker-compose.yaml:477-478) as the durable copy of
+ * the shard: copies all n = aur_stats.rows appended rows (tombstones included, live_out[i] = 0 for
+ * them) back to the host in append order.  Restore = aur_open + aur_add of the live rows, which also
+ * compacts the tombstones away.  user_out / org_out may be NULL. */
+int aur_export(aur_index* ix, void* rows_out, int64_t* ids_out, int32_t* user_out,
+               int32_t* org_out, uint8_t* live_out, int64_t n);
+
 /* Deletes.  Replaces collection.data.delete_many(where=...) (weaviate_client.py:309,
  * :336, :387): the Python layer resolves the filter to ids; rows become tombstones.
  * *removed receives how many ids were live. */

@@ -63,5 +63,17 @@ class OracleIndex:
         return O.cosine_topk(q, self.rows, k, ids=self.ids, live=self.live, row_user=self.user, row_org=self.org,
                              q_user=q_user, q_org=q_org)
 
+    def save(self, path):
+        np.savez(path, rows=self.rows[self.live], ids=self.ids[self.live], user=self.user[self.live], org=self.org[self.live],
+                 dim=self.dim, capacity=self.capacity)
+
+    @classmethod
+    def load(cls, path, capacity=None):
+        z = np.load(path if path.endswith(".npz") else path + ".npz")
+        ix = cls(int(z["dim"]), int(capacity or z["capacity"]))
+        if len(z["ids"]):
+            ix.add(z["rows"], z["ids"], z["user"], z["org"])
+        return ix
+
     def close(self):
         pass

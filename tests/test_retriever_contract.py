@@ -171,6 +171,27 @@ def test_private_client_facade_used_by_rca_prompt_builder(kb):
     assert resp.objects[0].metadata.score > 0
 
 
+def test_snapshot_roundtrip(tmp_path):
+    """save -> load keeps ids, tenant scope, upsert keys, the keyword leg; deleted chunks stay deleted."""
+    emb = HashEmbedder(64)
+    a = R.KnowledgeBase(emb, capacity=256, index_factory=lambda dim, cap: OracleIndex(dim, cap))
+    a.insert("u1", "d1", "a.md", _chunks("redis failover procedure", "postgres vacuum tuning", "kafka lag alert zx77"), "org")
+    a.insert("u2", "d2", "b.md", _chunks("unrelated notes"))
+    a.delete_where(lambda p: p["document_id"] == "d1" and p["chunk_index"] == 1)
+    before = [(o.properties["document_id"], o.properties["chunk_index"], round(o.metadata.score, 6))
+              for o in a.query("redis failover", 5, user_id="u1", alpha=0.5)]
+    a.save(str(tmp_path / "snap"))
+    b = R.KnowledgeBase.load(str(tmp_path / "snap"), emb, capacity=256, index_loader=lambda path, cap: OracleIndex.load(path, cap))
+    after = [(o.properties["document_id"], o.properties["chunk_index"], round(o.metadata.score, 6))
+             for o in b.query("redis failover", 5, user_id="u1", alpha=0.5)]
+    assert after == before and len(after) == 2
+    assert [o.properties["chunk_index"] for o in b.query("zx77", 3, user_id="u1", alpha=0.0)] == [2]
+    assert b.count_where(lambda p: p["document_id"] == "d1") == 2
+    assert b.query("unrelated", 3, user_id="u1", alpha=1.0)[0].properties["document_id"] == "d1"   # u2's chunk stays out of scope
+    assert b.insert("u1", "d1", "a.md", _chunks("redis failover procedure v2")) == 1               # same uuid5 key -> upsert
+    assert b.count_where(lambda p: p["document_id"] == "d1") == 2
+
+
 def test_filter_algebra():
     p = {"org_id": "o", "document_id": "discovery:1", "created_at": "2026-01-01T00:00:00+00:00"}
     assert Filter.by_property("org_id").equal("o").matches(p)
