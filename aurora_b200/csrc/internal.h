@@ -43,6 +43,8 @@ constexpr int kTcListMin = 64;     // list slots per query: max(ksel, this) so a
 constexpr int kTcMaxStages = 12;
 constexpr int kTcMaxDim = 768;     // A operand (queries) must fit 384 TMEM columns
 constexpr int kTcAccCol0 = 384;    // accumulator buffers at TMEM columns 384 / 448
+constexpr int kTcFifoRecs = 16;    // parked 4-score groups per thread before the deferred slow path runs
+constexpr int kTcFifoMaxKsel = 64; // (the FIFO shares shared memory with the candidate lists)
 constexpr int kSlack = 8;          // extra candidates kept for the exact re-rank
 constexpr int kMaxK = 128;
 

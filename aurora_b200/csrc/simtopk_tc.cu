@@ -64,8 +64,8 @@ constexpr int kThrWarps = 1;
 constexpr uint32_t kSlot = kTcQRows * 8u;   // byte stride between list slots of one query
 
 struct SmemLayout {
-  uint32_t stage_bytes, box_bytes, lcap;
-  uint32_t off_list, off_norm, off_bar, total;
+  uint32_t stage_bytes, box_bytes, lcap, fifo_recs;
+  uint32_t off_list, off_norm, off_fifo, off_bar, total;
 };
 __host__ __device__ inline SmemLayout make_layout(int cta_group, int epi_groups, int num_stages, int ksel) {
   SmemLayout L;
@@ -75,6 +75,9 @@ __host__ __device__ inline SmemLayout make_layout(int cta_group, int epi_groups,
   uint32_t o = L.stage_bytes * num_stages;
   L.off_list = o;   o += static_cast<uint32_t>(epi_groups) * L.lcap * kSlot;
   L.off_norm = o;   o += static_cast<uint32_t>(epi_groups) * 4u * 2u * kTcTileN * 4u;
+  // deferred-candidate FIFO: per thread kTcFifoRecs records of four adjacent scores (16 B) + a row tag
+  L.fifo_recs = (epi_groups == 1 && ksel <= kTcFifoMaxKsel) ? kTcFifoRecs : 0u;
+  L.off_fifo = o;   o += L.fifo_recs * kTcQRows * (16u + 4u);
   L.off_bar = o;    o += (2u * kTcMaxStages + 2u + 2u + 1u) * 8u + 16u;
   L.total = o;
   return L;
@@ -121,9 +124,13 @@ __device__ __noinline__ TopkState compact_list(TopkState st, uint32_t list_a, in
   return st;
 }
 
-// Admit one score into a query's list.
+// Admit one score into a query's list.  kTrackTop: also maintain the best two admitted scores (off when
+// the caller tracks the tile maxima itself).
+template <bool kTrackTop = true>
 __device__ __forceinline__ TopkState push_one(TopkState st, float s, int row, uint32_t list_a, int ksel, int lcap) {
-  if (s > st.top1) { st.top2 = st.top1; st.top1 = s; } else if (s > st.top2) st.top2 = s;
+  if constexpr (kTrackTop) {
+    if (s > st.top1) { st.top2 = st.top1; st.top1 = s; } else if (s > st.top2) st.top2 = s;
+  }
   const uint64_t key = make_key(s, row);
   if (st.nfill == lcap) st = compact_list(st, list_a, ksel);
   if (st.nfill < lcap) {
@@ -147,6 +154,28 @@ __device__ __noinline__ TopkState push_group4(TopkState st, float s0, float s1, 
   if (s1 >= st.tau) st = push_one(st, s1, row + 1, list_a, ksel, ksel);
   if (s2 >= st.tau) st = push_one(st, s2, row + 2, list_a, ksel, ksel);
   if (s3 >= st.tau) st = push_one(st, s3, row + 3, list_a, ksel, ksel);
+  return st;
+}
+
+// Deferred slow path.  The hot loop only parks a group of four adjacent scores whose max reached the
+// threshold (two predicated shared-memory stores); this routine runs when a thread's FIFO is nearly
+// full and once at the end, re-tests the parked scores against the threshold as it stands NOW (usually
+// much tighter) and admits the survivors.  The cold code is entered a handful of times per kernel
+// instead of ~100x per warp, and fewer scores pass.
+__device__ __noinline__ TopkState drain_fifo(TopkState st, uint32_t fifo_a, uint32_t ftag_a, int fcnt, uint32_t list_a,
+                                             int ksel) {
+#pragma unroll 1
+  for (int rec = 0; rec < fcnt; ++rec) {
+    int row;
+    float s0, s1, s2, s3;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(row) : "r"(ftag_a + rec * (kTcQRows * 4u)));
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(s0), "=f"(s1), "=f"(s2), "=f"(s3)
+                 : "r"(fifo_a + rec * (kTcQRows * 16u)));
+    if (s0 >= st.tau) st = push_one<false>(st, s0, row + 0, list_a, ksel, ksel);   // `>=` also rejects NaN
+    if (s1 >= st.tau) st = push_one<false>(st, s1, row + 1, list_a, ksel, ksel);
+    if (s2 >= st.tau) st = push_one<false>(st, s2, row + 2, list_a, ksel, ksel);
+    if (s3 >= st.tau) st = push_one<false>(st, s3, row + 3, list_a, ksel, ksel);
+  }
   return st;
 }
 
@@ -410,6 +439,11 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       }
       float* mynorm = normbuf + (warp - kThrWarps) * 2 * kTcTileN;
       const uint32_t list_a = smem_u32(smem + L.off_list) + (static_cast<uint32_t>(grp) * L.lcap * kTcQRows + r) * 8u;
+      // deferred-candidate FIFO (see drain_fifo); only with one published value per CTA (xm == 1)
+      const bool use_fifo = L.fifo_recs > 0 && xm == 1;
+      const uint32_t fifo_a = smem_u32(smem + L.off_fifo) + r * 16u;
+      const uint32_t ftag_a = smem_u32(smem + L.off_fifo) + L.fifo_recs * kTcQRows * 16u + r * 4u;
+      int fcnt = 0;
       TopkState st;
       st.min_key = kKeyEmpty; st.tau_local = -INFINITY; st.tau = -INFINITY;
       st.top1 = -INFINITY; st.top2 = -INFINITY; st.minpos = 0; st.nfill = 0;
@@ -542,6 +576,33 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         const long long t_ch0 = TCLK();
         // A group of four scores whose max reaches this query's threshold goes out of line.
         if (static_cast<uint32_t>(thr_e >> 32) == p.epoch) st.tau = fmaxf(st.tau, __uint_as_float(static_cast<uint32_t>(thr_e)));
+        if (use_fifo) {
+          st.top1 = fmaxf(st.top1, fmaxf(fmaxf(cmax[0], cmax[1]), fmaxf(cmax[2], cmax[3])));   // published below
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (cmax[c] >= st.tau) {
+              if (fcnt > static_cast<int>(L.fifo_recs) - 4) {   // no room for four more groups: make room (rare)
+                const long long t0 = TCLK();
+                st = drain_fifo(st, fifo_a, ftag_a, fcnt, list_a, ksel);
+                fcnt = 0;
+                ++nslow;
+                t_slow += TCLK() - t0;
+              }
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {   // park the groups that reach the threshold: two stores each, no call
+                const float m4 = fmaxf(fmaxf(__uint_as_float(acc[c][4 * g]), __uint_as_float(acc[c][4 * g + 1])),
+                                       fmaxf(__uint_as_float(acc[c][4 * g + 2]), __uint_as_float(acc[c][4 * g + 3])));
+                if (m4 >= st.tau) {
+                  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(fifo_a + static_cast<uint32_t>(fcnt) * (kTcQRows * 16u)),
+                               "r"(acc[c][4 * g]), "r"(acc[c][4 * g + 1]), "r"(acc[c][4 * g + 2]), "r"(acc[c][4 * g + 3]) : "memory");
+                  asm volatile("st.shared.b32 [%0], %1;" ::"r"(ftag_a + static_cast<uint32_t>(fcnt) * (kTcQRows * 4u)),
+                               "r"(row0 + c * 16 + 4 * g) : "memory");
+                  ++fcnt;
+                }
+              }
+            }
+          }
+        } else {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           if (cmax[c] >= st.tau) {
@@ -557,6 +618,7 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
             t_slow += TCLK() - t0;
           }
         }
+        }
 
         if (li < 8) t_top += TCLK() - t_ch0; else t_chunks += TCLK() - t_ch0;   // t_top reused: early tiles
         const long long t_pub0 = TCLK();
@@ -571,6 +633,13 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       t_loop_end = TCLK();
       __syncwarp();
       if (lane == 0) atomicAdd(const_cast<int*>(epi_done), 1);   // lets the threshold warps go
+      if (use_fifo) {   // whatever is still parked meets the final threshold below
+        float tau_fin = -INFINITY;
+        if (xchg && my_tiles > 0) tau_fin = read_threshold(thr_q, p.epoch);
+        st.tau = fmaxf(st.tau, tau_fin);
+        if (__any_sync(0xffffffffu, fcnt > 0)) st = drain_fifo(st, fifo_a, ftag_a, fcnt, list_a, ksel);
+        fcnt = 0;
+      }
 
       // ---- append the survivors (score >= the certified threshold, at most ksel of them)
       //      to this query's compact candidate row
