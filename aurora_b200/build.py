@@ -18,6 +18,7 @@ SOURCES = ["capi.cu", "kernels_simt.cu", "simtopk_tc.cu", "encoder.cu", "encoder
 HEADERS = ["internal.h", "ptx.cuh", os.path.join("..", "..", "include", "aurora_b200.h")]
 
 PROFILE = bool(int(os.environ.get("AUR_TC_PROFILE", "0")))   # bring-up timers in the tcgen05 kernel
+EXTRA_DEFS = os.environ.get("AUR_EXTRA_DEFS", "").split()     # e.g. -DAUR_ATTN_POLY_EVERY=0 for an A/B build
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -49,7 +50,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     objs = []
     for src in SOURCES:
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, *(["-DAUR_TC_PROFILE"] if PROFILE else []), "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *(["-DAUR_TC_PROFILE"] if PROFILE else []), *EXTRA_DEFS, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)

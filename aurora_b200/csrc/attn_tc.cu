@@ -140,8 +140,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p)
   long long pt[4] = {0, 0, 0, 0};
   const long long pt_begin = clock64();
 #endif
+  AttnItem next_item = blockIdx.x < total ? p.items[blockIdx.x / p.heads] : AttnItem{0, 1, 0, 0};
   for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-    const AttnItem item = p.items[w / p.heads];
+    const AttnItem item = next_item;      // fetched one iteration ahead: the L2 round trip is off the critical path
+    if (w + static_cast<int>(gridDim.x) < total) next_item = p.items[(w + gridDim.x) / p.heads];
     const int head = w % p.heads;
     const int nkb = (item.len + kKB - 1) / kKB;
     const uint32_t par = it & 1, prev = par ^ 1;

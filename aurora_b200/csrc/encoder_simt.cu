@@ -100,22 +100,35 @@ embed_ln_kernel(const int32_t* __restrict__ tok, const int32_t* __restrict__ pos
   ln_store(x, lane, chunks, hidden, g, b, eps, orow);
 }
 
+// Two rows per warp: both rows' loads are in flight before any arithmetic starts.
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ g, const float* __restrict__ b,
                  float eps, int n_rows, int hidden, __nv_bfloat16* __restrict__ out) {
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int row0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 2, lane = threadIdx.x & 31;
   ptx::grid_dep_launch();
   ptx::grid_dep_wait();
-  if (row >= n_rows) return;
+  if (row0 >= n_rows) return;
+  const bool two = row0 + 1 < n_rows;
   const int chunks = hidden >> 3;
-  const uint4* irow = reinterpret_cast<const uint4*>(in + static_cast<size_t>(row) * hidden);
-  float x[kMaxChunksPerLane][8];
+  const uint4* irow0 = reinterpret_cast<const uint4*>(in + static_cast<size_t>(row0) * hidden);
+  const uint4* irow1 = irow0 + chunks;
+  uint4 raw0[kMaxChunksPerLane], raw1[kMaxChunksPerLane];
 #pragma unroll
   for (int i = 0; i < kMaxChunksPerLane; ++i) {
     const int ch = lane + 32 * i;
-    if (ch < chunks) unpack8(__ldg(irow + ch), x[i]);
+    if (ch < chunks) { raw0[i] = __ldg(irow0 + ch); if (two) raw1[i] = __ldg(irow1 + ch); }
   }
-  ln_store(x, lane, chunks, hidden, g, b, eps, out + static_cast<size_t>(row) * hidden);
+  float x[kMaxChunksPerLane][8];
+#pragma unroll
+  for (int i = 0; i < kMaxChunksPerLane; ++i)
+    if (lane + 32 * i < chunks) unpack8(raw0[i], x[i]);
+  ln_store(x, lane, chunks, hidden, g, b, eps, out + static_cast<size_t>(row0) * hidden);
+  if (two) {
+#pragma unroll
+    for (int i = 0; i < kMaxChunksPerLane; ++i)
+      if (lane + 32 * i < chunks) unpack8(raw1[i], x[i]);
+    ln_store(x, lane, chunks, hidden, g, b, eps, out + static_cast<size_t>(row0 + 1) * hidden);
+  }
 }
 
 // Sentence vector per sequence: CLS row or mean over the real tokens, optional L2 normalisation
@@ -174,7 +187,7 @@ cudaError_t launch_embed_ln(const int32_t* tok, const int32_t* pos, int n_tok, i
 cudaError_t launch_layernorm(const __nv_bfloat16* in, const float* g, const float* b, float eps, int n_rows, int hidden,
                              __nv_bfloat16* out, cudaStream_t s) {
   if (n_rows <= 0) return cudaSuccess;
-  return launch_pdl(layernorm_kernel, dim3((n_rows + 7) / 8), dim3(256), 0, s, 1, in, g, b, eps, n_rows, hidden, out);
+  return launch_pdl(layernorm_kernel, dim3((n_rows + 15) / 16), dim3(256), 0, s, 1, in, g, b, eps, n_rows, hidden, out);
 }
 
 cudaError_t launch_pool(const __nv_bfloat16* x, const int32_t* cu, int n_seq, int hidden, int pool_mode, int normalize,
