@@ -163,7 +163,7 @@ reduce_lists_kernel(const uint64_t* __restrict__ in, int n_lists, int ksel, int 
 // --------------------------------------------------------------------------------------
 // Finalize: best ksel approximate candidates -> exact fp64 cosine -> (score desc, id asc).
 template <typename T>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(256, 2)
 finalize_kernel(FinalizeArgs a) {
   extern __shared__ uint64_t skeys[];
   __shared__ double ex_score[kMaxK + kSlack];
@@ -213,36 +213,55 @@ finalize_kernel(FinalizeArgs a) {
   __syncthreads();
   constexpr int kVec = 16 / static_cast<int>(sizeof(T));          // elements per 16-byte piece
   const bool vec_ok = (a.dim % kVec) == 0;
-  // two candidates per warp and step: both rows' loads are in flight before any arithmetic
-  for (int c0 = 2 * warp; c0 < ncand; c0 += 2 * nwarps) {
-    int32_t row[2]; const T* rv[2];
-    double dot[2] = {0.0, 0.0}, cc[2] = {0.0, 0.0};
+  // kRe candidates per warp and step, strided by the warp count, with every row load (and the id load)
+  // issued before any arithmetic: at k+slack = 40 and 16 warps all candidate rows of the query are in
+  // flight at once, so the gather costs one HBM round trip instead of one per pass.
+  constexpr int kRe = 3, kMaxCh = 4;                                // rows per step; 16-byte pieces per lane (dim <= 1024 bf16)
+  const int n_chunks = vec_ok ? a.dim / kVec : 0;
+  const bool reg_path = vec_ok && n_chunks <= 32 * kMaxCh;
+  for (int c0 = warp; c0 < ncand; c0 += kRe * nwarps) {
+    int32_t row[kRe]; const T* rv[kRe]; int64_t idv[kRe];
+    double dot[kRe], cc[kRe];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const uint64_t key = (c0 + h < ncand) ? topkeys[c0 + h] : 0ull;
+    for (int h = 0; h < kRe; ++h) {
+      const int c = c0 + h * nwarps;
+      const uint64_t key = (c < ncand) ? topkeys[c] : 0ull;
       row[h] = (key == 0) ? -1 : key_row(key);
       rv[h] = rows + static_cast<size_t>(row[h] < 0 ? 0 : row[h]) * a.dim;
+      dot[h] = 0.0; cc[h] = 0.0;
     }
-    if (vec_ok) {
-      for (int ch = lane; ch < a.dim / kVec; ch += 32) {
-        uint4 raw[2];
+    if (reg_path) {
+      uint4 raw[kRe][kMaxCh];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) raw[h] = (row[h] >= 0) ? __ldg(reinterpret_cast<const uint4*>(rv[h]) + ch) : make_uint4(0, 0, 0, 0);
+      for (int h = 0; h < kRe; ++h)
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          T el[kVec];
-          memcpy(el, &raw[h], 16);
+        for (int i = 0; i < kMaxCh; ++i) {
+          const int ch = lane + 32 * i;
+          raw[h][i] = (row[h] >= 0 && ch < n_chunks) ? __ldg(reinterpret_cast<const uint4*>(rv[h]) + ch) : make_uint4(0, 0, 0, 0);
+        }
 #pragma unroll
-          for (int e = 0; e < kVec; ++e) {
-            const double x = static_cast<double>(qs[ch * kVec + e]), y = static_cast<double>(to_f32(el[e]));
-            dot[h] = fma(x, y, dot[h]); cc[h] = fma(y, y, cc[h]);
+      for (int h = 0; h < kRe; ++h) idv[h] = (row[h] >= 0) ? __ldg(a.ids + row[h]) : -1;
+#pragma unroll
+      for (int h = 0; h < kRe; ++h)
+#pragma unroll
+        for (int i = 0; i < kMaxCh; ++i) {
+          const int ch = lane + 32 * i;
+          if (ch < n_chunks) {
+            T el[kVec];
+            memcpy(el, &raw[h][i], 16);
+#pragma unroll
+            for (int e = 0; e < kVec; ++e) {
+              const double x = static_cast<double>(qs[ch * kVec + e]), y = static_cast<double>(to_f32(el[e]));
+              dot[h] = fma(x, y, dot[h]); cc[h] = fma(y, y, cc[h]);
+            }
           }
         }
-      }
     } else {
+#pragma unroll
+      for (int h = 0; h < kRe; ++h) idv[h] = (row[h] >= 0) ? __ldg(a.ids + row[h]) : -1;
       for (int i = lane; i < a.dim; i += 32) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < kRe; ++h) {
           if (row[h] < 0) continue;
           const double x = static_cast<double>(qs[i]), y = static_cast<double>(to_f32(rv[h][i]));
           dot[h] = fma(x, y, dot[h]); cc[h] = fma(y, y, cc[h]);
@@ -250,16 +269,17 @@ finalize_kernel(FinalizeArgs a) {
       }
     }
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (c0 + h >= ncand) break;
+    for (int h = 0; h < kRe; ++h) {
+      const int c = c0 + h * nwarps;
+      if (c >= ncand) break;
       double sc = -INFINITY; int64_t id = -1;
       if (row[h] >= 0) {   // warp-uniform
         const double d = warp_sum_lane0(dot[h]), n2 = warp_sum_lane0(cc[h]);
         const double den = sqrt(s_qq) * sqrt(n2);
         sc = den > 0.0 ? d / den : 0.0;  // zero norm -> 0.0 (similarity.py:94-95)
-        id = a.ids[row[h]];
+        id = idv[h];
       }
-      if (lane == 0) { ex_score[c0 + h] = sc; ex_id[c0 + h] = id; }
+      if (lane == 0) { ex_score[c] = sc; ex_id[c] = id; }
     }
   }
   __syncthreads();
@@ -415,8 +435,8 @@ cudaError_t launch_finalize(const FinalizeArgs& a_in, cudaStream_t s) {
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
   }
-  if (a.dtype == 0) finalize_kernel<__nv_bfloat16><<<a.nq, 512, smem, s>>>(a);
-  else finalize_kernel<float><<<a.nq, 512, smem, s>>>(a);
+  if (a.dtype == 0) finalize_kernel<__nv_bfloat16><<<a.nq, 256, smem, s>>>(a);
+  else finalize_kernel<float><<<a.nq, 256, smem, s>>>(a);
   return cudaGetLastError();
 }
 
