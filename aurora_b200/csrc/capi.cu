@@ -149,7 +149,10 @@ int build_tmaps(aur_index* ix) {
 }
 
 bool tc_shape_ok(const aur_index* ix, int k, bool filtered) {
-  return ix->tmap_ok && !filtered && k <= kMaxK;
+  if (!ix->tmap_ok || filtered || k > kMaxK) return false;
+  // candidate lists (k + slack per query) and, past 768 dims, part of the queries share the SM's
+  // shared memory with the TMA ring: large k at large dim leaves no room for a pipeline
+  return tc_pick_stages(1, 1, k + kSlack, ix->dim, ix->smem_optin) >= 2;   // (one-CTA tiles: the tail block of a batch)
 }
 
 // Runs one block of <= 256 queries through the tcgen05 kernel.  Leaves candidate keys in
@@ -163,9 +166,9 @@ int run_tc_block(aur_index* ix, int cta_group, const void* q_dev, int nqb, int k
   // epilogue groups: 1 by default; 2 (alternating tiles) stays selectable for experiments
   int epi_groups = ix->opt_epi_groups;
   if (epi_groups == 0) epi_groups = 1;   // measured: one group + a deeper TMA ring (11 stages) beats two groups + 8
-  const int stages = tc_pick_stages(cta_group, epi_groups, ksel, ix->smem_optin);
+  const int stages = tc_pick_stages(cta_group, epi_groups, ksel, ix->dim, ix->smem_optin);
   if (stages < 2) return fail(AUR_ERR_UNSUPPORTED, "k too large for the tcgen05 path's shared memory");
-  const size_t smem = tc_smem_bytes(cta_group, epi_groups, stages, ksel);
+  const size_t smem = tc_smem_bytes(cta_group, epi_groups, stages, ksel, ix->dim);
   const int n_lists = n_tsets * epi_groups;   // candidate lists per query
   const size_t ncand = static_cast<size_t>(n_qblocks) * kTcQRows * n_lists * ksel;
   CU_TRY(ix->cand_a.reserve(ncand));
@@ -207,7 +210,8 @@ int search_dev_locked(aur_index* ix, const void* q_dev, int nq, int k, const int
   int kernel = ix->opt_kernel;
   if (kernel == AUR_KERNEL_AUTO) kernel = tc_shape_ok(ix, k, filtered) ? AUR_KERNEL_TC2 : AUR_KERNEL_SIMT;
   if (kernel != AUR_KERNEL_SIMT && !tc_shape_ok(ix, k, filtered))
-    return fail(AUR_ERR_UNSUPPORTED, "tcgen05 path needs bf16, dim %% 64 == 0, dim <= %d, no tenant filter", kTcMaxDim);
+    return fail(AUR_ERR_UNSUPPORTED, "tcgen05 path needs bf16, dim %% 64 == 0, dim <= %d, no tenant filter, and k small enough "
+                "for its shared-memory lists at this dim", kTcMaxDim);
   ix->last_kernel = kernel;
   ix->last_launches = 0;
   CU_TRY(cudaEventRecord(ix->ev_begin, s));

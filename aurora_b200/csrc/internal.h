@@ -41,7 +41,8 @@ constexpr int kTcQRows = 128;      // queries per CTA (TMEM lanes)
 constexpr int kTcChunk = 16;       // scores examined per threshold test
 constexpr int kTcListMin = 64;     // list slots per query: max(ksel, this) so a whole first tile appends
 constexpr int kTcMaxStages = 12;
-constexpr int kTcMaxDim = 768;     // A operand (queries) must fit 384 TMEM columns
+constexpr int kTcTmemDim = 768;    // query dims resident in TMEM (384 columns); dims beyond live in shared memory
+constexpr int kTcMaxDim = 1024;    // largest dim served by the tcgen05 path
 constexpr int kTcAccCol0 = 384;    // accumulator buffers at TMEM columns 384 / 448
 constexpr int kTcFifoRecs = 16;    // parked 4-score groups per thread before the deferred slow path runs
 constexpr int kTcFifoMaxKsel = 64; // (the FIFO shares shared memory with the candidate lists)
@@ -67,8 +68,8 @@ constexpr int kTcPubMax = 74;      // published values a thread folds into its t
 
 // epi_groups: 1 = four epilogue warps take every tile; 2 = two sets of four alternate tiles
 // (each set owns one TMEM accumulator buffer and its own candidate lists).
-size_t tc_smem_bytes(int cta_group, int epi_groups, int num_stages, int ksel);
-int tc_pick_stages(int cta_group, int epi_groups, int ksel, size_t smem_limit);
+size_t tc_smem_bytes(int cta_group, int epi_groups, int num_stages, int ksel, int dim);
+int tc_pick_stages(int cta_group, int epi_groups, int ksel, int dim, size_t smem_limit);
 // Launches the fused similarity + top-k kernel.  tmap: CUtensorMap over the corpus with a
 // {64, 64 / cta_group} box and 128-byte swizzle.
 cudaError_t tc_launch(int cta_group, int epi_groups, int grid, const void* tmap, const TcParams& p, size_t smem,

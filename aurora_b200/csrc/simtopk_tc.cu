@@ -64,15 +64,19 @@ constexpr int kThrWarps = 1;
 constexpr uint32_t kSlot = kTcQRows * 8u;   // byte stride between list slots of one query
 
 struct SmemLayout {
-  uint32_t stage_bytes, box_bytes, lcap, fifo_recs;
-  uint32_t off_list, off_norm, off_fifo, off_bar, total;
+  uint32_t stage_bytes, box_bytes, lcap, fifo_recs, qs_kb;
+  uint32_t off_qs, off_list, off_norm, off_fifo, off_bar, total;
 };
-__host__ __device__ inline SmemLayout make_layout(int cta_group, int epi_groups, int num_stages, int ksel) {
+__host__ __device__ inline SmemLayout make_layout(int cta_group, int epi_groups, int num_stages, int ksel, int dim) {
   SmemLayout L;
   L.box_bytes = (kTcTileN / cta_group) * 128u;
   L.stage_bytes = L.box_bytes * kTcKbPerStage;
   L.lcap = static_cast<uint32_t>(ksel);
   uint32_t o = L.stage_bytes * num_stages;
+  // query dims beyond the 768 that fit TMEM: [128 queries x 64] bf16 K-major SWIZZLE_128B tiles, one per
+  // 64-dim k-block (the SS-MMA A operand); 1024-byte aligned because the stages are
+  L.qs_kb = dim > kTcTmemDim ? static_cast<uint32_t>((dim - kTcTmemDim) / kTcKBlock) : 0u;
+  L.off_qs = o;     o += L.qs_kb * (kTcQRows * 128u);
   L.off_list = o;   o += static_cast<uint32_t>(epi_groups) * L.lcap * kSlot;
   L.off_norm = o;   o += static_cast<uint32_t>(epi_groups) * 4u * 2u * kTcTileN * 4u;
   // deferred-candidate FIFO: per thread kTcFifoRecs records of four adjacent scores (16 B) + a row tag
@@ -234,7 +238,7 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   // shared-address-space inference, i.e. LDS/STS instead of generic loads.
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
-  const SmemLayout L = make_layout(kCtaGroup, kEpiGroups, p.num_stages, p.ksel);
+  const SmemLayout L = make_layout(kCtaGroup, kEpiGroups, p.num_stages, p.ksel, p.dim);
   float* normbuf = reinterpret_cast<float*>(smem + L.off_norm);      // [4 warps][2][64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);
   uint64_t* full_bar = bars;                              // [kTcMaxStages]
@@ -357,10 +361,21 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
             for (int j = 0; j < kTcKbPerStage; ++j) {
               if (j < nkb && !(p.dbg_flags & 2)) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {  // 4 x K=16 per 128-byte k-block
-                  const uint32_t acc = (j | k) != 0 ? 1u : (kb0 != 0 ? 1u : 0u);
-                  mma_ts_bf16<kCtaGroup>(d_tmem, a_col + j * 32 + k * 8, pack_u64(base_lo + j * kBox16 + k * 2, kDescHi),
-                                         idesc, acc);
+                const int kb = kb0 + j;
+                if (kb < kTcTmemDim / kTcKBlock) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {  // 4 x K=16 per 128-byte k-block, queries from TMEM
+                    const uint32_t acc = (j | k) != 0 ? 1u : (kb0 != 0 ? 1u : 0u);
+                    mma_ts_bf16<kCtaGroup>(d_tmem, a_col + j * 32 + k * 8, pack_u64(base_lo + j * kBox16 + k * 2, kDescHi),
+                                           idesc, acc);
+                  }
+                } else {                         // dims past 768: queries from shared memory (SS)
+                  const uint32_t qs_lo = ((smem_u32(smem + L.off_qs) & 0x3FFFFu) >> 4) +
+                                         static_cast<uint32_t>(kb - kTcTmemDim / kTcKBlock) * ((kTcQRows * 128u) >> 4);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    mma_ss_bf16<kCtaGroup>(d_tmem, pack_u64(qs_lo + k * 2, kDescHi), pack_u64(base_lo + j * kBox16 + k * 2, kDescHi),
+                                           idesc, 1u);
                 }
               }
             }
@@ -427,10 +442,19 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
             v[i >> 2][(i & 3) * 4 + 0] = x.x; v[i >> 2][(i & 3) * 4 + 1] = x.y;
             v[i >> 2][(i & 3) * 4 + 2] = x.z; v[i >> 2][(i & 3) * 4 + 3] = x.w;
           }
-          tmem_st_x16(lane_addr + kb * 32, v[0]);
-          tmem_st_x16(lane_addr + kb * 32 + 16, v[1]);
+          if (kb < kTcTmemDim / kTcKBlock) {
+            tmem_st_x16(lane_addr + kb * 32, v[0]);
+            tmem_st_x16(lane_addr + kb * 32 + 16, v[1]);
+          } else {   // K-major tile with the 128-byte swizzle TMA would have produced: 16-byte chunk c of row r at c ^ (r & 7)
+            uint8_t* qrow = smem + L.off_qs + static_cast<uint32_t>(kb - kTcTmemDim / kTcKBlock) * (kTcQRows * 128u) + r * 128u;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<uint4*>(qrow + ((c ^ (r & 7)) << 4)) =
+                  make_uint4(v[c >> 2][(c & 3) * 4 + 0], v[c >> 2][(c & 3) * 4 + 1], v[c >> 2][(c & 3) * 4 + 2], v[c >> 2][(c & 3) * 4 + 3]);
+          }
         }
         tmem_wait_st();
+        fence_proxy_async_smem();   // (shared-memory part of the queries -> visible to the tensor core)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -688,13 +712,13 @@ cudaError_t launch_variant(const cudaLaunchConfig_t& cfg, const CUtensorMap& tm,
 
 }  // namespace
 
-size_t tc_smem_bytes(int cta_group, int epi_groups, int num_stages, int ksel) {
-  return make_layout(cta_group, epi_groups, num_stages, ksel).total + 1024;  // + alignment slack
+size_t tc_smem_bytes(int cta_group, int epi_groups, int num_stages, int ksel, int dim) {
+  return make_layout(cta_group, epi_groups, num_stages, ksel, dim).total + 1024;  // + alignment slack
 }
 
-int tc_pick_stages(int cta_group, int epi_groups, int ksel, size_t smem_limit) {
+int tc_pick_stages(int cta_group, int epi_groups, int ksel, int dim, size_t smem_limit) {
   for (int s = kTcMaxStages; s >= 2; --s)
-    if (tc_smem_bytes(cta_group, epi_groups, s, ksel) <= smem_limit) return s;
+    if (tc_smem_bytes(cta_group, epi_groups, s, ksel, dim) <= smem_limit) return s;
   return 0;
 }
 

@@ -95,6 +95,8 @@ def test_simt_tenant_filter_and_tombstones():
 @pytest.mark.parametrize("n,d,nq,k", [
     (30000, 768, 256, 32), (9000, 384, 100, 10), (50001, 512, 200, 100), (20000, 768, 300, 5),
     (777, 64, 1, 1), (12345, 256, 129, 128), (64, 768, 256, 32), (5000, 768, 128, 64),
+    # dims past 768: the first 768 dims of the queries sit in TMEM, the rest in shared memory (SS MMAs)
+    (20000, 1024, 256, 32), (9000, 1024, 300, 64), (7000, 896, 130, 10), (4000, 832, 64, 5),
 ])
 def test_tcgen05_parity(kernel, n, d, nq, k):
     C, Q = _data(n, d, nq, seed=n % 1000 + nq + d)
@@ -103,6 +105,23 @@ def test_tcgen05_parity(kernel, n, d, nq, k):
         ix.set_kernel(kernel)
         ids, sc = ix.search(Q, k)
         assert ix.stats()["last_kernel"] == kernel
+    _check(ids, sc, *O.cosine_topk(Q, C, k))
+
+
+def test_large_k_at_dim_1024_falls_back_in_auto_mode():
+    """cfg4's shape class (dim 1024, top-100): the lists (k + slack per query) plus the shared-memory part of
+    the queries leave no room for a TMA ring, so AUTO serves it with the generic kernel and an explicit
+    tcgen05 request is refused."""
+    n, d, nq, k = 6000, 1024, 70, 100
+    C, Q = _data(n, d, nq, seed=5)
+    with Index(d, n) as ix:
+        ix.add(C, np.arange(n, dtype=np.int64))
+        ids, sc = ix.search(Q, k)
+        assert ix.stats()["last_kernel"] == N.KERNEL_SIMT
+        ix.set_kernel(N.KERNEL_TC2)
+        with pytest.raises(N.AuroraError) as e:
+            ix.search(Q, k)
+        assert e.value.code == N.AUR_ERR_UNSUPPORTED
     _check(ids, sc, *O.cosine_topk(Q, C, k))
 
 
