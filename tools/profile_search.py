@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Tiny driver for ncu: build the cfg2 corpus (1M x 768 bf16) and run a few searches.
 
-  python tools/profile_search.py [tc2|tc1|simt|auto] [n_rows] [nq] [k] [reps]
+  [AUR_DIM=1024] python tools/profile_search.py [tc2|tc1|simt|auto] [n_rows] [nq] [k] [reps]
 numpy + ctypes only.
 """
 
@@ -24,7 +24,7 @@ def main():
     nq = int(sys.argv[3]) if len(sys.argv) > 3 else 256
     k = int(sys.argv[4]) if len(sys.argv) > 4 else 32
     reps = int(sys.argv[5]) if len(sys.argv) > 5 else 5
-    d = 768
+    d = int(os.environ.get("AUR_DIM", "768"))
     rng = np.random.default_rng(1002)
     block = to_bf16_bits(rng.standard_normal((min(n, 50_000), d)).astype(np.float32))
     q = to_bf16_bits(np.random.default_rng(2002).standard_normal((nq, d)).astype(np.float32))
