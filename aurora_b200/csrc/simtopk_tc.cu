@@ -471,6 +471,7 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       TopkState st;
       st.min_key = kKeyEmpty; st.tau_local = -INFINITY; st.tau = -INFINITY;
       st.top1 = -INFINITY; st.top2 = -INFINITY; st.minpos = 0; st.nfill = 0;
+      if (qglob >= p.nq) st.tau = INFINITY;   // padding row of a partial query block: admits nothing, appends nothing
       float published = -INFINITY;
       int nslow = 0;
       long long t_wait = 0, t_slow = 0, t_ld = 0, t_top = 0, t_fast = 0, t_chunks = 0, t_pub = 0;
@@ -674,7 +675,7 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       {
         const size_t cap = static_cast<size_t>(n_tsets) * kEpiGroups * ksel;
         uint64_t* out = p.cand + static_cast<size_t>(qglob) * cap;
-        if (st.nfill > 0) {
+        if (st.nfill > 0 && qglob < p.nq) {
           const uint32_t slot0 = atomicAdd(p.cand_count + qglob, static_cast<uint32_t>(st.nfill));
           for (int t = 0; t < st.nfill; ++t) out[slot0 + t] = lds_u64(list_a + t * kSlot);
         }

@@ -299,3 +299,19 @@ def test_export_save_load_roundtrip(tmp_path):
         assert st["rows"] == st["live"] == int(live.sum())
         got = ix2.search(Q, k)
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+
+
+@pytest.mark.parametrize("nq", [1, 130, 200])
+def test_partial_query_blocks_stay_correct_over_many_launches(nq):
+    """A batch that does not fill its last 128-query block leaves padding rows in the kernel; they must not
+    accumulate candidates across launches (their counters are never reset by the finalize step)."""
+    n, d, k = 30000, 768, 32
+    C, Q = _data(n, d, nq, seed=nq)
+    want = O.cosine_topk(Q, C, k)
+    with Index(d, n) as ix:
+        ix.add(C, np.arange(n, dtype=np.int64))
+        for kern in (N.KERNEL_TC2, N.KERNEL_TC1):
+            ix.set_kernel(kern)
+            for _ in range(40):
+                ids, sc = ix.search(Q, k)
+            _check(ids, sc, *want)
