@@ -152,15 +152,19 @@ bool tc_shape_ok(const aur_index* ix, int k, bool filtered) {
   if (!ix->tmap_ok || filtered || k > kMaxK) return false;
   // candidate lists (k + slack per query) and, past 768 dims, part of the queries share the SM's
   // shared memory with the TMA ring: large k at large dim leaves no room for a pipeline
-  return tc_pick_stages(1, 1, k + kSlack, ix->dim, ix->smem_optin) >= 2;   // (one-CTA tiles: the tail block of a batch)
+  return tc_pick_stages(2, 1, k + kSlack, ix->dim, ix->smem_optin) >= 2;
 }
 
 // Runs one block of <= 256 queries through the tcgen05 kernel.  Leaves candidate keys in
 // ix->cand_a as [nqb_pad, n_lists, ksel]; returns n_lists.
 int run_tc_block(aur_index* ix, int cta_group, const void* q_dev, int nqb, int ksel, float* dbg, int* n_lists_out,
                  cudaStream_t s) {
-  const int n_qblocks = (nqb > kTcQRows) ? 2 : 1;
-  if (cta_group == 2 && n_qblocks != 2) cta_group = 1;  // a pair needs 256 query rows
+  int n_qblocks = (nqb > kTcQRows) ? 2 : 1;
+  if (cta_group == 2 && n_qblocks != 2) {
+    // a pair works on 256 query rows.  A short tail block normally runs as single CTAs; when their larger
+    // TMA stages do not fit next to the lists (large k at dim > 768) it runs as a pair with a padding block
+    if (tc_pick_stages(1, 1, ksel, ix->dim, ix->smem_optin) >= 2) cta_group = 1; else n_qblocks = 2;
+  }
   int grid = ix->sm_count & ~1;
   const int n_tsets = (cta_group == 2) ? grid / 2 : grid / n_qblocks;
   // epilogue groups: 1 by default; 2 (alternating tiles) stays selectable for experiments

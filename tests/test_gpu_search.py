@@ -109,10 +109,10 @@ def test_tcgen05_parity(kernel, n, d, nq, k):
 
 
 def test_large_k_at_dim_1024_falls_back_in_auto_mode():
-    """cfg4's shape class (dim 1024, top-100): the lists (k + slack per query) plus the shared-memory part of
+    """dim 1024 with k = 128: the lists (k + slack per query) plus the shared-memory part of
     the queries leave no room for a TMA ring, so AUTO serves it with the generic kernel and an explicit
     tcgen05 request is refused."""
-    n, d, nq, k = 6000, 1024, 70, 100
+    n, d, nq, k = 6000, 1024, 70, 128
     C, Q = _data(n, d, nq, seed=5)
     with Index(d, n) as ix:
         ix.add(C, np.arange(n, dtype=np.int64))
@@ -122,6 +122,19 @@ def test_large_k_at_dim_1024_falls_back_in_auto_mode():
         with pytest.raises(N.AuroraError) as e:
             ix.search(Q, k)
         assert e.value.code == N.AUR_ERR_UNSUPPORTED
+    _check(ids, sc, *O.cosine_topk(Q, C, k))
+
+
+@pytest.mark.parametrize("nq", [70, 300, 512])
+def test_cfg4_shape_class_dim1024_top100_on_tcgen05(nq):
+    """BASELINE config 4's shape class (dim 1024, top-100): served by CTA pairs; a short tail block of the
+    batch runs as a pair with a padding query block because single-CTA stages no longer fit."""
+    n, d, k = 9000, 1024, 100
+    C, Q = _data(n, d, nq, seed=nq + 1)
+    with Index(d, n) as ix:
+        ix.add(C, np.arange(n, dtype=np.int64))
+        ids, sc = ix.search(Q, k)
+        assert ix.stats()["last_kernel"] == N.KERNEL_TC2
     _check(ids, sc, *O.cosine_topk(Q, C, k))
 
 
