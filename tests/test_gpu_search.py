@@ -328,3 +328,21 @@ def test_partial_query_blocks_stay_correct_over_many_launches(nq):
             for _ in range(40):
                 ids, sc = ix.search(Q, k)
             _check(ids, sc, *want)
+
+
+def test_sharded_searcher_single_rank_on_gpu():
+    """aurora_b200.sharded.make_gpu_searcher (the wiring bench.py's N > 1 path uses) at world size 1:
+    local search + device merge must reproduce Index.search."""
+    torch = pytest.importorskip("torch")
+    from aurora_b200.sharded import make_gpu_searcher
+
+    n, d, nq, k = 20000, 768, 64, 16
+    C, Q = _data(n, d, nq, seed=3)
+    with Index(d, n) as ix:
+        ix.add(C, np.arange(n, dtype=np.int64))
+        want_ids, want_sc = ix.search(Q, k)
+        q_dev = torch.from_numpy(to_bf16_bits(Q).view(np.int16)).cuda()
+        ids, sc = make_gpu_searcher(ix, world=1, device=0).search(q_dev, k)
+        torch.cuda.synchronize()
+    assert np.array_equal(ids.cpu().numpy(), want_ids)
+    assert np.array_equal(sc.cpu().numpy(), want_sc)
