@@ -346,3 +346,47 @@ def test_sharded_searcher_single_rank_on_gpu():
         torch.cuda.synchronize()
     assert np.array_equal(ids.cpu().numpy(), want_ids)
     assert np.array_equal(sc.cpu().numpy(), want_sc)
+
+
+def test_concurrent_ingest_and_search_threads():
+    """BASELINE config 5's access pattern in miniature: one thread appends chunk batches while others search
+    (the reference is hit from gunicorn threads and Celery workers at once; every entry point takes the
+    shard's mutex).  Every answer must be a valid top-k of SOME prefix of the appended rows: ids below the
+    row count seen after the call, scores non-increasing, and the planted exact match on top once present."""
+    import threading
+
+    d, k, batches, per = 768, 8, 24, 512
+    rng = np.random.default_rng(11)
+    Q = O.round_to_bf16(rng.standard_normal((32, d)).astype(np.float32))
+    blocks = [O.round_to_bf16(rng.standard_normal((per, d)).astype(np.float32)) for _ in range(batches)]
+    blocks[5][7] = Q[3]                                    # exact match appears with batch 5 (id 5*512+7)
+    errors, done = [], threading.Event()
+    with Index(d, batches * per) as ix:
+        def writer():
+            try:
+                for b, blk in enumerate(blocks):
+                    ix.add(blk, np.arange(b * per, (b + 1) * per, dtype=np.int64))
+            except Exception as e:      # pragma: no cover
+                errors.append(e)
+            finally:
+                done.set()
+
+        def reader():
+            try:
+                while not done.is_set():
+                    ids, sc = ix.search(Q, k)
+                    rows_after = ix.stats()["rows"]
+                    valid = ids >= 0
+                    assert np.all(ids[valid] < rows_after)
+                    assert np.all(np.diff(np.where(valid, sc, -np.inf), axis=1) <= 1e-6)
+                    if rows_after >= 6 * per and valid[3, 0] and (ids[3] == 5 * per + 7).any():
+                        assert ids[3, 0] == 5 * per + 7 and sc[3, 0] > 0.9999
+            except Exception as e:      # pragma: no cover
+                errors.append(e)
+
+        ts = [threading.Thread(target=writer)] + [threading.Thread(target=reader) for _ in range(3)]
+        [t.start() for t in ts]; [t.join() for t in ts]
+        assert not errors, errors[0]
+        ids, sc = ix.search(Q, k)
+        C = np.concatenate(blocks)
+    _check(ids, sc, *O.cosine_topk(Q, C, k))
