@@ -7,6 +7,10 @@ rng = np.random.default_rng(7)
 n_seq, heads = 64, 12
 hidden = heads * 64
 lens = np.clip(np.rint(rng.normal(384, 96, n_seq)), 16, 512).astype(np.int64)
+if os.environ.get('AUR_LEN'):
+    lens[:] = int(os.environ['AUR_LEN'])
+if os.environ.get('AUR_NSEQ'):
+    n_seq = int(os.environ['AUR_NSEQ']); lens = np.resize(lens, n_seq)
 cu = np.zeros(n_seq + 1, np.int32); cu[1:] = np.cumsum(lens)
 T = int(cu[-1])
 qkv = to_bf16_bits((rng.standard_normal((T, 3 * hidden)) * 1.0).astype(np.float32))
