@@ -1,0 +1,75 @@
+"""Property tests (hypothesis) of the host-side text machinery: BM25 index invariants, ranked fusion,
+WordPiece robustness on arbitrary unicode, snapshot of the keyword index under upserts / deletes."""
+
+import math
+
+import pytest
+
+hyp = pytest.importorskip("hypothesis")
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+from aurora_b200.bm25 import BM25Index, ranked_fusion, tokenize  # noqa: E402
+from aurora_b200.wordpiece import WordPieceTokenizer, basic_tokenize  # noqa: E402
+
+words = st.sampled_from(["redis", "kafka", "lag", "cpu", "disk", "pod", "alert", "node", "zx9981", "latency", "p99"])
+docs = st.lists(st.lists(words, min_size=1, max_size=12).map(" ".join), min_size=1, max_size=12)
+
+
+@settings(max_examples=60, deadline=None)
+@given(docs, st.lists(words, min_size=1, max_size=4).map(" ".join))
+def test_bm25_scores_sorted_positive_and_only_matching_docs(texts, query):
+    ix = BM25Index()
+    for i, t in enumerate(texts):
+        ix.add(i, t)
+    res = ix.search(query, 100)
+    qt = set(tokenize(query))
+    assert all(s > 0 and math.isfinite(s) for _, s in res)
+    assert [s for _, s in res] == sorted((s for _, s in res), reverse=True)
+    assert {d for d, _ in res} == {i for i, t in enumerate(texts) if qt & set(tokenize(t))}
+    assert ix.search(query, 3) == res[:3]                                  # limit is a prefix
+
+
+@settings(max_examples=40, deadline=None)
+@given(docs)
+def test_bm25_upsert_and_remove_leave_no_trace(texts):
+    a, b = BM25Index(), BM25Index()
+    for i, t in enumerate(texts):
+        a.add(i, t)
+        b.add(i, "placeholder text that will be replaced")
+        b.add(i, t)                                                        # upsert = same as fresh insert
+    b.add(999, "temporary document about redis kafka cpu")
+    assert b.remove(999)
+    for q in ("redis", "kafka lag", "cpu disk pod", "placeholder", "temporary"):
+        ra, rb = a.search(q, 50), b.search(q, 50)
+        assert [d for d, _ in ra] == [d for d, _ in rb]
+        assert all(abs(x - y) < 1e-12 for (_, x), (_, y) in zip(ra, rb))
+    assert len(a) == len(b) == len(texts)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.integers(0, 30), unique=True, max_size=20), st.lists(st.integers(0, 30), unique=True, max_size=20),
+       st.floats(0.0, 1.0), st.integers(1, 10))
+def test_ranked_fusion_properties(dense, sparse, alpha, limit):
+    fused = ranked_fusion([(alpha, dense), (1.0 - alpha, sparse)], limit)
+    ids = [d for d, _ in fused]
+    assert len(ids) == len(set(ids)) <= limit
+    assert [s for _, s in fused] == sorted((s for _, s in fused), reverse=True)
+    contributing = (set(dense) if alpha > 0 else set()) | (set(sparse) if alpha < 1 else set())
+    assert set(ids) <= contributing
+    for d, s in fused:                                                     # score = sum of weight / (rank + 60)
+        want = (alpha / (dense.index(d) + 60) if d in dense and alpha > 0 else 0.0) + \
+               ((1 - alpha) / (sparse.index(d) + 60) if d in sparse and alpha < 1 else 0.0)
+        assert abs(s - want) < 1e-12
+    if alpha == 1.0:
+        assert ids == dense[:limit]
+
+
+@settings(max_examples=80, deadline=None)
+@given(st.text(max_size=200))
+def test_wordpiece_never_crashes_and_respects_limits(text):
+    vocab = {t: i for i, t in enumerate(["[PAD]", "[UNK]", "[CLS]", "[SEP]", "a", "b", "##a", "##b", "the", "##s", "!", "."])}
+    tok = WordPieceTokenizer(vocab)
+    ids = tok.encode(text, max_len=16)
+    assert 2 <= len(ids) <= 16 and ids[0] == vocab["[CLS]"] and ids[-1] == vocab["[SEP]"]
+    assert all(0 <= i < len(vocab) for i in ids)
+    assert all(w and not any(c.isspace() for c in w) for w in basic_tokenize(text))
