@@ -131,7 +131,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = 125_000
+    sample = int(os.environ.get("AUR_BENCH_SAMPLE", "125000"))   # rows per step (the contract test shrinks it)
     for _ in range(args.warmup):
         cpu_flat_search_qps(sample)
     vals = [cpu_flat_search_qps(sample)[0] for _ in range(args.steps)]
