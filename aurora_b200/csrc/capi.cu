@@ -120,6 +120,7 @@ struct aur_index {
   DevBuf<uint32_t> cand_count;   // compacted candidates per query (self-resetting)
   uint32_t epoch = 0;
   DevBuf<float> score_chunk;
+  DevBuf<float> masked_inv;      // inverse norms with one tenant's invisible rows turned into NaN
   DevBuf<uint8_t> stage_q;       // host-entry staging: queries
   DevBuf<int32_t> stage_quser, stage_qorg;
   DevBuf<float> stage_scores;
@@ -158,7 +159,7 @@ bool tc_shape_ok(const aur_index* ix, int k, bool filtered) {
 // Runs one block of <= 256 queries through the tcgen05 kernel.  Leaves candidate keys in
 // ix->cand_a as [nqb_pad, n_lists, ksel]; returns n_lists.
 int run_tc_block(aur_index* ix, int cta_group, const void* q_dev, int nqb, int ksel, float* dbg, int* n_lists_out,
-                 cudaStream_t s) {
+                 cudaStream_t s, const float* inv_norm = nullptr) {
   int n_qblocks = (nqb > kTcQRows) ? 2 : 1;
   if (cta_group == 2 && n_qblocks != 2) {
     // a pair works on 256 query rows.  A short tail block normally runs as single CTAs; when their larger
@@ -188,7 +189,7 @@ int run_tc_block(aur_index* ix, int cta_group, const void* q_dev, int nqb, int k
   if (++ix->epoch == 0) ix->epoch = 1;
   TcParams p;
   p.q = static_cast<const __nv_bfloat16*>(q_dev);
-  p.inv_norm = ix->d_inv_norm;
+  p.inv_norm = inv_norm ? inv_norm : ix->d_inv_norm;
   p.cand = ix->cand_a.p;
   p.cand_count = ix->cand_count.p;
   p.dbg_scores = dbg;
@@ -204,12 +205,14 @@ int run_tc_block(aur_index* ix, int cta_group, const void* q_dev, int nqb, int k
   return AUR_OK;
 }
 
+// uniform_scope (nullable): {user, org} when the host knows every query of the batch carries the same tenant scope;
+// the filter then folds into the row scale and the tcgen05 kernel serves the batch.
 int search_dev_locked(aur_index* ix, const void* q_dev, int nq, int k, const int32_t* q_user, const int32_t* q_org,
-                      float* scores, int64_t* ids, double* scores64, cudaStream_t s) {
+                      float* scores, int64_t* ids, double* scores64, cudaStream_t s, const int32_t* uniform_scope = nullptr) {
   if (nq <= 0 || k <= 0) return fail(AUR_ERR_INVALID, "nq and k must be positive");
   if (k > kMaxK) return fail(AUR_ERR_UNSUPPORTED, "k > %d", kMaxK);
   if (nq > 65535) return fail(AUR_ERR_UNSUPPORTED, "nq > 65535: split the batch");
-  const bool filtered = q_user != nullptr;
+  const bool filtered = q_user != nullptr && uniform_scope == nullptr;   // per-query scopes: generic kernel only
   const int ksel = k + kSlack;
   int kernel = ix->opt_kernel;
   if (kernel == AUR_KERNEL_AUTO) kernel = tc_shape_ok(ix, k, filtered) ? AUR_KERNEL_TC2 : AUR_KERNEL_SIMT;
@@ -220,6 +223,14 @@ int search_dev_locked(aur_index* ix, const void* q_dev, int nq, int k, const int
   ix->last_launches = 0;
   CU_TRY(cudaEventRecord(ix->ev_begin, s));
   bool k_timed = false;
+  const float* tc_inv = nullptr;
+  if (kernel != AUR_KERNEL_SIMT && q_user != nullptr && ix->rows > 0) {   // one scope for the whole batch
+    CU_TRY(ix->masked_inv.reserve(static_cast<size_t>(ix->capacity) + 64));
+    CU_TRY(launch_mask_inv_norm(ix->d_inv_norm, ix->d_user, ix->d_org, uniform_scope[0], uniform_scope[1], ix->rows,
+                                ix->masked_inv.p, s));
+    ++ix->last_launches;
+    tc_inv = ix->masked_inv.p;
+  }
 
   const int qstep = (kernel == AUR_KERNEL_SIMT) ? 1024 : 2 * kTcQRows;
   for (int q0 = 0; q0 < nq; q0 += qstep) {
@@ -252,7 +263,7 @@ int search_dev_locked(aur_index* ix, const void* q_dev, int nq, int k, const int
       cur = ix->cand_a.p;
     } else {
       if (!k_timed) CU_TRY(cudaEventRecord(ix->ev_k0, s));
-      int rc = run_tc_block(ix, kernel == AUR_KERNEL_TC1 ? 1 : 2, qb, nqb, ksel, nullptr, &n_lists, s);
+      int rc = run_tc_block(ix, kernel == AUR_KERNEL_TC1 ? 1 : 2, qb, nqb, ksel, nullptr, &n_lists, s, tc_inv);
       if (rc != AUR_OK) return rc;
       if (!k_timed) { CU_TRY(cudaEventRecord(ix->ev_k1, s)); k_timed = true; }
       ix->last_launches += 1;
@@ -383,7 +394,7 @@ int aur_close(aur_index* ix) {
   cudaSetDevice(ix->device);
   if (ix->stream) cudaStreamSynchronize(ix->stream);
   cudaFree(ix->d_rows); cudaFree(ix->d_inv_norm); cudaFree(ix->d_ids); cudaFree(ix->d_user); cudaFree(ix->d_org);
-  ix->cand_a.release(); ix->cand_b.release(); ix->pub.release(); ix->cand_count.release(); ix->score_chunk.release(); ix->stage_q.release();
+  ix->cand_a.release(); ix->cand_b.release(); ix->pub.release(); ix->cand_count.release(); ix->score_chunk.release(); ix->masked_inv.release(); ix->stage_q.release();
   ix->stage_quser.release(); ix->stage_qorg.release(); ix->stage_scores.release(); ix->stage_ids.release();
   ix->dbg.release();
   if (ix->ev_begin) cudaEventDestroy(ix->ev_begin);
@@ -521,7 +532,16 @@ int aur_search(aur_index* ix, const void* queries_host, int32_t nq, int32_t k, c
       dorg = ix->stage_qorg.p;
     }
   }
-  int rc = search_dev_locked(ix, ix->stage_q.p, nq, k, du, dorg, ix->stage_scores.p, ix->stage_ids.p, nullptr, s);
+  // the reference asks one tenant's question at a time (weaviate_client.py:244-249): when every query of the
+  // batch carries the same (user, org) scope the filter folds into the row scale and the tcgen05 kernel serves it
+  int32_t scope[2] = {0, -1};
+  bool uniform = q_user != nullptr;
+  if (uniform) {
+    scope[0] = q_user[0]; scope[1] = q_org ? q_org[0] : -1;
+    for (int i = 1; i < nq && uniform; ++i) uniform = q_user[i] == scope[0] && (q_org ? q_org[i] : -1) == scope[1];
+  }
+  int rc = search_dev_locked(ix, ix->stage_q.p, nq, k, du, dorg, ix->stage_scores.p, ix->stage_ids.p, nullptr, s,
+                             uniform ? scope : nullptr);
   if (rc != AUR_OK) return rc;
   // straight into the caller's buffers (async when they are pinned); nothing is written
   // unless every kernel above was enqueued successfully

@@ -112,6 +112,10 @@ cudaError_t launch_merge_topk(const double* in_s, const int64_t* in_ids, size_t 
 cudaError_t launch_cosine_pairs(const float* a, const float* b, int64_t n, int dim, int clamp, double* out,
                                 cudaStream_t s);
 cudaError_t launch_fill_f32(float* p, float v, int64_t n, cudaStream_t s);
+// out[i] = visible(user u, org o) ? inv[i] : NaN  -- lets the tcgen05 kernel serve a batch whose queries all
+// carry the same tenant scope
+cudaError_t launch_mask_inv_norm(const float* inv, const int32_t* row_user, const int32_t* row_org, int32_t u, int32_t o,
+                                 int64_t n, float* out, cudaStream_t s);
 
 // ---------------------------------------------------------------- encoder (BERT-family forward)
 // out = epi(A . W^T + bias): A [m_tiles*128, K] bf16 (TMA box {64,128}), W [N, K] bf16 (TMA box {64,BN}).

@@ -457,6 +457,25 @@ cudaError_t launch_cosine_pairs(const float* a, const float* b, int64_t n, int d
   return cudaGetLastError();
 }
 
+// Tenant scope folded into the row scale: rows the (user, org) pair may not see get NaN, which the
+// tcgen05 kernel treats exactly like a tombstone (never admitted, never published).  Same predicate
+// as simt_scores_kernel: row_user == u OR (o >= 0 AND row_org == o)  (weaviate_client.py:244-249).
+__global__ void mask_inv_norm_kernel(const float* __restrict__ inv, const int32_t* __restrict__ row_user,
+                                     const int32_t* __restrict__ row_org, int32_t u, int32_t o, int64_t n,
+                                     float* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bool ok = (row_user[i] == u) || (o >= 0 && row_org[i] == o);
+  out[i] = ok ? inv[i] : __uint_as_float(0x7FC00000u);
+}
+
+cudaError_t launch_mask_inv_norm(const float* inv, const int32_t* row_user, const int32_t* row_org, int32_t u, int32_t o,
+                                 int64_t n, float* out, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  mask_inv_norm_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(inv, row_user, row_org, u, o, n, out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_fill_f32(float* p, float v, int64_t n, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
   fill_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(p, v, n);

@@ -117,7 +117,9 @@ int aur_remove(aur_index* ix, const int64_t* ids, int64_t n, int64_t* removed);
 /* Search.  Replaces the dense leg of collection.query.hybrid (weaviate_client.py:252-259)
  * and collection.query.near_text (incident_feedback/weaviate_client.py:286-291), batched:
  * nq queries at once, top-k each.  q_user / q_org: per-query tenant codes (NULL q_user =
- * unfiltered; q_org may be NULL or hold -1 for "no org").
+ * unfiltered; q_org may be NULL or hold -1 for "no org").  When every query of the batch
+ * carries the same scope (the reference's call pattern) the tensor-core kernel serves it;
+ * mixed scopes fall back to the generic kernel.
  * scores_out [nq*k] float, ids_out [nq*k] int64. */
 int aur_search(aur_index* ix, const void* queries_host, int32_t nq, int32_t k,
                const int32_t* q_user, const int32_t* q_org,

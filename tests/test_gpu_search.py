@@ -90,6 +90,36 @@ def test_simt_tenant_filter_and_tombstones():
     _check(ids, sc, *O.cosine_topk(Q, C, k, live=live, row_user=ru, row_org=ro, q_user=qu, q_org=qo))
 
 
+@pytest.mark.parametrize("with_org", [False, True])
+def test_uniform_tenant_scope_is_served_by_the_tcgen05_kernel(with_org):
+    """The reference asks one tenant's question at a time (user_id == u OR org_id == o,
+    weaviate_client.py:244-249): with one scope for the whole batch the filter folds into the row scale
+    and the tensor-core kernel serves it; mixed scopes in one batch stay on the generic kernel."""
+    n, d, nq, k = 30000, 768, 70, 16
+    C, Q = _data(n, d, nq, seed=99)
+    rng = np.random.default_rng(5)
+    ru = rng.integers(0, 40, n).astype(np.int32)
+    ro = rng.integers(-1, 6, n).astype(np.int32)
+    live = np.ones(n, dtype=bool)
+    qu = np.full(nq, 7, np.int32)
+    qo = np.full(nq, 3 if with_org else -1, np.int32)
+    with Index(d, n) as ix:
+        ix.add(C, np.arange(n, dtype=np.int64), ru, ro)
+        gone = np.nonzero(ru == 7)[0][:5].astype(np.int64)           # tombstones inside the tenant's rows
+        ix.remove(gone); live[gone] = False
+        ids, sc = ix.search(Q, k, qu, qo)
+        assert ix.stats()["last_kernel"] == N.KERNEL_TC2
+        _check(ids, sc, *O.cosine_topk(Q, C, k, live=live, row_user=ru, row_org=ro, q_user=qu, q_org=qo))
+        vis = (ru[ids[ids >= 0]] == 7) | ((qo[0] >= 0) & (ro[ids[ids >= 0]] == qo[0]))
+        assert vis.all()
+        qu2 = qu.copy(); qu2[1] = 8                                    # two different scopes in one batch
+        ids2, sc2 = ix.search(Q, k, qu2, qo)
+        assert ix.stats()["last_kernel"] == N.KERNEL_SIMT
+        _check(ids2, sc2, *O.cosine_topk(Q, C, k, live=live, row_user=ru, row_org=ro, q_user=qu2, q_org=qo))
+        none = ix.search(Q, k, np.full(nq, 1234, np.int32), np.full(nq, -1, np.int32))   # a tenant with no rows
+        assert (none[0] == -1).all()
+
+
 # ------------------------------------------------------------------ tcgen05 path
 @pytest.mark.parametrize("kernel", [N.KERNEL_TC1, N.KERNEL_TC2])
 @pytest.mark.parametrize("n,d,nq,k", [
