@@ -64,3 +64,15 @@ def test_backend_failure_is_reported_not_swallowed_for_insert(daemon):
     with pytest.raises(RuntimeError):
         kb.insert_chunks("u", "d", "f", _chunks("x"))          # Celery retries (weaviate_client.py:210-212)
     assert kb.search_knowledge_base("u", "q") == []
+
+
+def test_bootstrap_requires_its_variables(monkeypatch):
+    from aurora_b200 import bootstrap
+
+    monkeypatch.delenv("AURORA_B200_ENCODER_WEIGHTS", raising=False)
+    monkeypatch.delenv("AURORA_B200_VOCAB", raising=False)
+    with pytest.raises(RuntimeError, match="AURORA_B200_ENCODER_WEIGHTS"):
+        bootstrap.configure_from_env()
+    with pytest.raises(ValueError):
+        bootstrap._model_config("gpt-2")
+    assert bootstrap._model_config("minilm-l6").hidden == 384
