@@ -257,3 +257,66 @@ def test_retriever_with_cuda_encoder_end_to_end():
     finally:
         R.configure(encoder=None)
         enc.close()
+
+
+def test_bootstrap_from_environment_end_to_end(tmp_path, monkeypatch):
+    """aurora_b200.bootstrap.configure_from_env: safetensors checkpoint (HF names) + vocab.txt -> CUDA encoder
+    + shard behind the reference's module API, then snapshot -> restore.  all-MiniLM-L6-v2 dimensions
+    (the model the reference deploys), random-init weights written to a temporary checkpoint."""
+    import json
+    import struct
+
+    from aurora_b200 import bootstrap, retriever as R
+
+    cfg_o = B.MINILM_L6
+    w = B.init_weights(cfg_o, seed=7, bf16=True)
+    h = cfg_o.hidden
+    hf = {"embeddings.word_embeddings.weight": w["word_emb"], "embeddings.position_embeddings.weight": w["pos_emb"],
+          "embeddings.token_type_embeddings.weight": w["type_emb"], "embeddings.LayerNorm.weight": w["emb_ln_g"],
+          "embeddings.LayerNorm.bias": w["emb_ln_b"]}
+    for l in range(cfg_o.layers):
+        p, q = f"l{l}.", f"encoder.layer.{l}."
+        for i, n in enumerate(("query", "key", "value")):
+            hf[q + f"attention.self.{n}.weight"] = w[p + "wqkv"][i * h:(i + 1) * h]
+            hf[q + f"attention.self.{n}.bias"] = w[p + "bqkv"][i * h:(i + 1) * h]
+        for a, b in (("attention.output.dense.weight", "wo"), ("attention.output.dense.bias", "bo"),
+                     ("attention.output.LayerNorm.weight", "ln1_g"), ("attention.output.LayerNorm.bias", "ln1_b"),
+                     ("intermediate.dense.weight", "wi"), ("intermediate.dense.bias", "bi"), ("output.dense.weight", "wo2"),
+                     ("output.dense.bias", "bo2"), ("output.LayerNorm.weight", "ln2_g"), ("output.LayerNorm.bias", "ln2_b")):
+            hf[q + a] = w[p + b]
+    header, blobs, off = {}, [], 0
+    for name, arr in hf.items():
+        raw = np.ascontiguousarray(arr, dtype="<f4").tobytes()
+        header[name] = {"dtype": "F32", "shape": list(arr.shape), "data_offsets": [off, off + len(raw)]}
+        blobs.append(raw); off += len(raw)
+    hj = json.dumps(header).encode()
+    ckpt = tmp_path / "model.safetensors"
+    with open(ckpt, "wb") as f:
+        f.write(struct.pack("<Q", len(hj))); f.write(hj)
+        for b_ in blobs:
+            f.write(b_)
+    words = ["restart", "the", "payment", "service", "when", "latency", "spikes", "rotate", "database", "credentials",
+             "kafka", "consumer", "lag", "alert", "runbook", "every", "ninety", "days"]
+    vocab = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"] + words
+    vocab += [f"[unused{i}]" for i in range(cfg_o.vocab - len(vocab))]
+    (tmp_path / "vocab.txt").write_text("\n".join(vocab) + "\n", encoding="utf-8")
+    snap = tmp_path / "snap"
+    for k_, v_ in {"AURORA_B200_MODEL": "minilm-l6", "AURORA_B200_ENCODER_WEIGHTS": str(ckpt), "AURORA_B200_VOCAB": str(tmp_path / "vocab.txt"),
+                   "AURORA_B200_CAPACITY": "512", "AURORA_B200_MAX_TOKENS": "4096", "AURORA_B200_MAX_SEQS": "32",
+                   "AURORA_B200_SNAPSHOT": str(snap)}.items():
+        monkeypatch.setenv(k_, v_)
+    try:
+        bootstrap.configure_from_env()
+        chunks = [{"content": "restart the payment service when latency spikes", "heading_context": "", "chunk_index": 0},
+                  {"content": "rotate database credentials every ninety days", "heading_context": "", "chunk_index": 1},
+                  {"content": "kafka consumer lag alert runbook", "heading_context": "", "chunk_index": 2}]
+        assert R.insert_chunks("u1", "doc", "runbook.md", chunks) == 3
+        top = R.search_knowledge_base("u1", "kafka consumer lag alert runbook", limit=2, alpha=1.0)
+        assert top[0]["chunk_index"] == 2 and top[0]["score"] > 0.999
+        R._get_kb().save(str(snap))
+        bootstrap.configure_from_env()                     # restores the snapshot
+        again = R.search_knowledge_base("u1", "kafka consumer lag alert runbook", limit=2, alpha=1.0)
+        assert [(r["chunk_index"], round(r["score"], 5)) for r in again] == [(r["chunk_index"], round(r["score"], 5)) for r in top]
+        assert R.get_document_chunk_count("u1", "doc") == 3
+    finally:
+        R.configure(encoder=None)
