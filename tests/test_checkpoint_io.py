@@ -52,3 +52,18 @@ def test_safetensors_to_encoder_weights(tmp_path):
     for name in got:
         tol = 1e-3 if name == "type_emb" else 0.0          # the F16 tensor is not bf16-exact
         np.testing.assert_allclose(got[name], w[name], rtol=0, atol=tol, err_msg=name)
+
+
+def test_pack_sequences_and_presets():
+    from aurora_b200.encoder import BGE_BASE, BGE_LARGE, MINILM_L6, pack_sequences
+
+    tok, cu = pack_sequences([[101, 5, 102], [101, 102], [101, 7, 8, 9, 102]])
+    assert tok.dtype == np.int32 and cu.dtype == np.int32
+    assert tok.tolist() == [101, 5, 102, 101, 102, 101, 7, 8, 9, 102] and cu.tolist() == [0, 3, 5, 10]
+    assert (BGE_BASE.hidden, BGE_BASE.heads, BGE_BASE.layers, BGE_BASE.pool) == (768, 12, 12, "cls")
+    assert (MINILM_L6.hidden, MINILM_L6.heads, MINILM_L6.layers, MINILM_L6.pool) == (384, 12, 6, "mean")   # head dim 32
+    assert BGE_LARGE.hidden // BGE_LARGE.heads == 64
+    # the oracle's presets describe the same architectures
+    for mine, theirs in ((BGE_BASE, B.BGE_BASE), (MINILM_L6, B.MINILM_L6), (BGE_LARGE, B.BGE_LARGE)):
+        assert (mine.hidden, mine.layers, mine.heads, mine.inter, mine.vocab, mine.pool) == \
+               (theirs.hidden, theirs.layers, theirs.heads, theirs.inter, theirs.vocab, theirs.pool)
