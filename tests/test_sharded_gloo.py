@@ -84,9 +84,9 @@ def test_shard_bounds_cover_all_rows():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
 
 
-@pytest.mark.timeout(120)
-def test_two_rank_gloo_matches_single_process(tmp_path):
-    world = 2
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("world", [2, 3])     # 3: shards of unequal size
+def test_multi_rank_gloo_matches_single_process(tmp_path, world):
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     q, c = _corpus()
     want_ids, want_sc = O.cosine_topk(q, c, K)
