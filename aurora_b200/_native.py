@@ -21,8 +21,9 @@ KERNEL_NAMES = {0: "auto", 1: "simt", 2: "tcgen05-cta1", 3: "tcgen05-cta2"}
 # every symbol include/aurora_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "aur_abi_version", "aur_last_error", "aur_device_count", "aur_open", "aur_close", "aur_get_stats",
-    "aur_set_option", "aur_sync", "aur_add", "aur_add_dev", "aur_export", "aur_remove", "aur_search", "aur_search_dev",
-    "aur_merge_topk_dev", "aur_merge_topk_packed_dev", "aur_cosine_pairs", "aur_dev_malloc", "aur_dev_free", "aur_memcpy_h2d", "aur_memcpy_d2h",
+    "aur_set_option", "aur_sync", "aur_add", "aur_add_dev", "aur_export", "aur_compact", "aur_remove", "aur_search", "aur_search_ex", "aur_search_subset", "aur_search_dev",
+    "aur_merge_topk_dev", "aur_merge_topk_packed_dev", "aur_exchange_create", "aur_exchange_connect", "aur_exchange_close",
+    "aur_exchange_status", "aur_search_exchange_dev", "aur_cosine_pairs", "aur_dev_malloc", "aur_dev_free", "aur_memcpy_h2d", "aur_memcpy_d2h",
     "aur_debug_tc_scores",
     "aur_encoder_open", "aur_encoder_close", "aur_encoder_load", "aur_encode", "aur_encode_append",
     "aur_encoder_get_stats", "aur_debug_gemm", "aur_debug_attention", "aur_debug_encoder_hidden",
@@ -89,10 +90,18 @@ def load():
         "aur_add_dev": (C.c_int, [vp, vp, vp, vp, vp, i64, vp]),
         "aur_export": (C.c_int, [vp, vp, vp, vp, vp, vp, i64]),
         "aur_remove": (C.c_int, [vp, vp, i64, C.POINTER(i64)]),
+        "aur_compact": (C.c_int, [vp, C.POINTER(i64)]),
+        "aur_search_ex": (C.c_int, [vp, vp, i32, i32, vp, vp, vp, vp, C.POINTER(i64)]),
+        "aur_search_subset": (C.c_int, [vp, vp, i32, i32, vp, i64, vp, vp]),
         "aur_search": (C.c_int, [vp, vp, i32, i32, vp, vp, vp, vp]),
         "aur_search_dev": (C.c_int, [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]),
         "aur_merge_topk_dev": (C.c_int, [i32, vp, vp, i32, i32, i32, vp, vp, vp, vp]),
         "aur_merge_topk_packed_dev": (C.c_int, [i32, vp, i32, i32, i32, vp, vp, vp, vp]),
+        "aur_exchange_create": (C.c_int, [i32, i32, i32, i32, i32, C.POINTER(vp), vp]),
+        "aur_exchange_connect": (C.c_int, [vp, vp]),
+        "aur_exchange_close": (C.c_int, [vp]),
+        "aur_exchange_status": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i32)]),
+        "aur_search_exchange_dev": (C.c_int, [vp, vp, vp, i32, i32, vp, vp, vp]),
         "aur_cosine_pairs": (C.c_int, [i32, vp, vp, i64, i32, i32, vp]),
         "aur_dev_malloc": (C.c_int, [i32, C.c_uint64, C.POINTER(vp)]),
         "aur_dev_free": (C.c_int, [i32, vp]),

@@ -43,25 +43,30 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build_native(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build_native(force: bool = False, verbose: bool = False, out: str = "", tag: str = "") -> str:
+    """out / tag: A/B builds (``AUR_EXTRA_DEFS=... python -m aurora_b200.build --out lib_b.so --tag b``) land beside
+    the product library and are selected at run time with AURORA_B200_LIB."""
+    lib = os.path.join(HERE, out) if out else LIB
+    if not out and not force and not _stale():
         return LIB
     nvcc = _nvcc()
     objs = []
     for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        obj = os.path.join(CSRC, src.replace(".cu", (f".{tag}" if tag else "") + ".o"))
         cmd = [nvcc, *NVCC_FLAGS, *(["-DAUR_TC_PROFILE"] if PROFILE else []), *EXTRA_DEFS, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)
         subprocess.run(cmd, check=True)
         objs.append(obj)
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", *objs, "-o", LIB, "-cudart", "static"]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", *objs, "-o", lib, "-cudart", "static"]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.run(cmd, check=True)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build_native(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    def _opt(name):
+        return sys.argv[sys.argv.index(name) + 1] if name in sys.argv else ""
+    print(build_native(force="--force" in sys.argv, verbose="-v" in sys.argv, out=_opt("--out"), tag=_opt("--tag")))

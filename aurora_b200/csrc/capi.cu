@@ -5,6 +5,16 @@
 //   ids       [capacity] i64   caller ids;  user / org [capacity] i32 tenant codes
 // plus grow-only scratch for candidate lists.  No CPU compute path exists here: without
 // a CUDA device every entry point fails with AUR_ERR_NO_DEVICE.
+//
+// Concurrency (BASELINE config 5: streaming ingest while queries run; the reference's callers are 8 gunicorn
+// threads + 4 Celery children, docker-compose.yaml:191,283-285).  The shard is append-only with a PUBLISHED row
+// count: a writer copies rows / ids / tenant codes / inverse norms into [rows_pub, rows_pub + n) on the ingest
+// stream, waits for them to land, and only then stores rows_pub + n (release).  A search loads rows_pub once
+// (acquire) when it is enqueued and scans exactly that prefix -- rows behind it are masked by the kernels' own
+// n_rows bound -- so every answer is the top-k of a consistent prefix, which it can report
+// (aur_search_ex).  Searches never take the writers' lock; each in-flight search owns a SearchCtx (candidate
+// lists, threshold-exchange table, staging buffers, events, stream), so several can be enqueued at once.
+// Compaction and export are the only exclusive operations.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -12,9 +22,13 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <unordered_map>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/aurora_b200.h"
@@ -93,10 +107,47 @@ int encode_tmap_2d_bf16(void* tmap, const void* base, uint64_t cols, uint64_t ro
 }
 }  // namespace aur
 
+// Scratch and bookkeeping of ONE in-flight search.  Device-pointer searches are bound to the caller's stream
+// (same stream -> same context -> stream order protects the scratch); host-buffer searches take a context from a
+// pool and run on its own stream, so N threads can search at once.
+struct SearchCtx {
+  std::mutex mu;                  // one enqueue at a time
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t bound = nullptr;   // caller stream this context serves (nullptr = pool context)
+  cudaEvent_t ev_begin = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_end = nullptr;
+  bool have_timing = false;
+  int last_kernel = 0, last_launches = 0;
+  int64_t snapshot_rows = 0;
+  uint32_t epoch = 0;
+  DevBuf<uint64_t> cand_a, cand_b;
+  DevBuf<uint64_t> pub;          // tcgen05 kernel's cross-CTA threshold exchange
+  DevBuf<uint32_t> cand_count;   // compacted candidates per query (self-resetting)
+  DevBuf<float> score_chunk;
+  DevBuf<float> masked_inv;      // inverse norms with the invisible rows turned into NaN (tenant scope / id subset)
+  DevBuf<int32_t> allow_rows;    // subset search: rows that stay visible
+  DevBuf<uint8_t> stage_q;       // host-entry staging: queries
+  DevBuf<int32_t> stage_quser, stage_qorg;
+  DevBuf<float> stage_scores;
+  DevBuf<int64_t> stage_ids;
+  void release() {
+    cand_a.release(); cand_b.release(); pub.release(); cand_count.release(); score_chunk.release(); masked_inv.release();
+    allow_rows.release(); stage_q.release(); stage_quser.release(); stage_qorg.release(); stage_scores.release();
+    stage_ids.release();
+    if (ev_begin) cudaEventDestroy(ev_begin);
+    if (ev_k0) cudaEventDestroy(ev_k0);
+    if (ev_k1) cudaEventDestroy(ev_k1);
+    if (ev_end) cudaEventDestroy(ev_end);
+    if (own_stream) cudaStreamDestroy(own_stream);
+  }
+};
+
 struct aur_index {
-  std::mutex mu;
+  std::shared_mutex rw;          // shared: searches and appends; exclusive: compaction, export, close
+  std::mutex mu;                 // host metadata: id2row, live, options, the context pool
+  std::mutex mu_write;           // one writer at a time (append / remove)
   int device = 0, dim = 0, dtype = 0;
-  int64_t capacity = 0, rows = 0, live = 0;
+  int64_t capacity = 0, live = 0;
+  std::atomic<int64_t> rows_pub{0};   // rows visible to searches (published after the data landed)
   size_t elt = 2;
   void* d_rows = nullptr;
   float* d_inv_norm = nullptr;
@@ -104,9 +155,8 @@ struct aur_index {
   int32_t* d_user = nullptr;
   int32_t* d_org = nullptr;
   std::unordered_map<int64_t, int64_t> id2row;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev_begin = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_end = nullptr;
-  bool have_timing = false;
+  cudaStream_t stream = nullptr;         // the index's own stream: device-pointer calls with stream == NULL
+  cudaStream_t ingest_stream = nullptr;  // host appends / tombstones, lowest priority so queries overtake them
   CUtensorMap tmap[2];  // box rows 64 (cta_group::1) and 32 (cta_group::2)
   bool tmap_ok = false;
   int sm_count = 0;
@@ -114,18 +164,9 @@ struct aur_index {
   int opt_kernel = AUR_KERNEL_AUTO;
   int opt_dbg_flags = 0;
   int opt_epi_groups = 0;        // 0 = auto
-  int last_kernel = 0, last_launches = 0;
-  DevBuf<uint64_t> cand_a, cand_b;
-  DevBuf<uint64_t> pub;          // tcgen05 kernel's cross-CTA threshold exchange
-  DevBuf<uint32_t> cand_count;   // compacted candidates per query (self-resetting)
-  uint32_t epoch = 0;
-  DevBuf<float> score_chunk;
-  DevBuf<float> masked_inv;      // inverse norms with one tenant's invisible rows turned into NaN
-  DevBuf<uint8_t> stage_q;       // host-entry staging: queries
-  DevBuf<int32_t> stage_quser, stage_qorg;
-  DevBuf<float> stage_scores;
-  DevBuf<int64_t> stage_ids;
-  DevBuf<float> dbg;
+  std::vector<std::unique_ptr<SearchCtx>> ctxs;
+  std::vector<SearchCtx*> free_ctxs;   // idle pool contexts
+  SearchCtx* last_ctx = nullptr;       // context of the most recently enqueued search (aur_get_stats)
 };
 
 namespace {
@@ -156,10 +197,43 @@ bool tc_shape_ok(const aur_index* ix, int k, bool filtered) {
   return tc_pick_stages(2, 1, k + kSlack, ix->dim, ix->smem_optin) >= 2;
 }
 
-// Runs one block of <= 256 queries through the tcgen05 kernel.  Leaves candidate keys in
-// ix->cand_a as [nqb_pad, n_lists, ksel]; returns n_lists.
-int run_tc_block(aur_index* ix, int cta_group, const void* q_dev, int nqb, int ksel, float* dbg, int* n_lists_out,
-                 cudaStream_t s, const float* inv_norm = nullptr) {
+int ctx_init(aur_index* ix, SearchCtx* c) {
+  int lo = 0, hi = 0;
+  CU_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi = numerically lowest = highest priority
+  CU_TRY(cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, hi));
+  CU_TRY(cudaEventCreate(&c->ev_begin)); CU_TRY(cudaEventCreate(&c->ev_k0));
+  CU_TRY(cudaEventCreate(&c->ev_k1));    CU_TRY(cudaEventCreate(&c->ev_end));
+  (void)ix;
+  return AUR_OK;
+}
+
+// Context for a search on the caller's stream `s` (bound) or, with s == nullptr, an idle pool context.
+int acquire_ctx(aur_index* ix, cudaStream_t s, SearchCtx** out) {
+  std::lock_guard<std::mutex> lk(ix->mu);
+  if (s) {
+    for (auto& c : ix->ctxs)
+      if (c->bound == s) { *out = c.get(); return AUR_OK; }
+  } else if (!ix->free_ctxs.empty()) {
+    *out = ix->free_ctxs.back(); ix->free_ctxs.pop_back();
+    return AUR_OK;
+  }
+  std::unique_ptr<SearchCtx> c(new SearchCtx());
+  int rc = ctx_init(ix, c.get());
+  if (rc != AUR_OK) { c->release(); return rc; }
+  c->bound = s;
+  *out = c.get();
+  ix->ctxs.push_back(std::move(c));
+  return AUR_OK;
+}
+void release_ctx(aur_index* ix, SearchCtx* c) {
+  std::lock_guard<std::mutex> lk(ix->mu);
+  if (!c->bound) ix->free_ctxs.push_back(c);
+}
+
+// Runs one block of <= 256 queries through the tcgen05 kernel over the first n_rows rows.  Leaves candidate keys
+// in c->cand_a as [nqb_pad, n_lists, ksel]; returns n_lists.
+int run_tc_block(aur_index* ix, SearchCtx* c, int cta_group, const void* q_dev, int nqb, int ksel, int64_t n_rows, float* dbg,
+                 int* n_lists_out, cudaStream_t s, const float* inv_norm = nullptr) {
   int n_qblocks = (nqb > kTcQRows) ? 2 : 1;
   if (cta_group == 2 && n_qblocks != 2) {
     // a pair works on 256 query rows.  A short tail block normally runs as single CTAs; when their larger
@@ -176,60 +250,78 @@ int run_tc_block(aur_index* ix, int cta_group, const void* q_dev, int nqb, int k
   const size_t smem = tc_smem_bytes(cta_group, epi_groups, stages, ksel, ix->dim);
   const int n_lists = n_tsets * epi_groups;   // candidate lists per query
   const size_t ncand = static_cast<size_t>(n_qblocks) * kTcQRows * n_lists * ksel;
-  CU_TRY(ix->cand_a.reserve(ncand));
+  CU_TRY(c->cand_a.reserve(ncand));
   const size_t npub = static_cast<size_t>(n_qblocks) * kTcQRows * (((n_tsets + 1) & ~1) + 1);
-  if (npub > ix->pub.n) {
-    CU_TRY(ix->pub.reserve(npub));
-    CU_TRY(cudaMemsetAsync(ix->pub.p, 0, npub * 8, s));  // epoch 0 is never used by a launch
+  if (npub > c->pub.n) {
+    CU_TRY(c->pub.reserve(npub));
+    CU_TRY(cudaMemsetAsync(c->pub.p, 0, npub * 8, s));  // epoch 0 is never used by a launch
   }
-  if (ix->cand_count.n < 2 * kTcQRows) {
-    CU_TRY(ix->cand_count.reserve(2 * kTcQRows));
-    CU_TRY(cudaMemsetAsync(ix->cand_count.p, 0, 2 * kTcQRows * 4, s));
+  if (c->cand_count.n < 2 * kTcQRows) {
+    CU_TRY(c->cand_count.reserve(2 * kTcQRows));
+    CU_TRY(cudaMemsetAsync(c->cand_count.p, 0, 2 * kTcQRows * 4, s));
   }
-  if (++ix->epoch == 0) ix->epoch = 1;
+  if (++c->epoch == 0) c->epoch = 1;
   TcParams p;
   p.q = static_cast<const __nv_bfloat16*>(q_dev);
   p.inv_norm = inv_norm ? inv_norm : ix->d_inv_norm;
-  p.cand = ix->cand_a.p;
-  p.cand_count = ix->cand_count.p;
+  p.cand = c->cand_a.p;
+  p.cand_count = c->cand_count.p;
   p.dbg_scores = dbg;
-  p.pub = ix->pub.p;
-  p.epoch = ix->epoch;
-  p.n_rows = ix->rows;
+  p.pub = c->pub.p;
+  p.epoch = c->epoch;
+  p.n_rows = n_rows;
   p.nq = nqb; p.dim = ix->dim; p.ksel = ksel; p.n_lists = n_lists; p.n_qblocks = n_qblocks;
   p.num_stages = stages;
   p.dbg_flags = ix->opt_dbg_flags;
-  p.n_tiles = static_cast<int>((ix->rows + kTcTileN - 1) / kTcTileN);
+  p.n_tiles = static_cast<int>((n_rows + kTcTileN - 1) / kTcTileN);
   CU_TRY(tc_launch(cta_group, epi_groups, grid, &ix->tmap[cta_group - 1], p, smem, s));
   *n_lists_out = n_lists;
   return AUR_OK;
 }
 
-// uniform_scope (nullable): {user, org} when the host knows every query of the batch carries the same tenant scope;
-// the filter then folds into the row scale and the tcgen05 kernel serves the batch.
-int search_dev_locked(aur_index* ix, const void* q_dev, int nq, int k, const int32_t* q_user, const int32_t* q_org,
-                      float* scores, int64_t* ids, double* scores64, cudaStream_t s, const int32_t* uniform_scope = nullptr) {
+// Visibility of a search besides tombstones: per-query tenant codes (generic kernel), one tenant scope for the
+// whole batch, or an explicit list of visible rows -- the last two fold into the row scale (NaN = invisible), so
+// the tensor-core kernel serves them.
+struct Scope {
+  const int32_t* q_user = nullptr;       // device, per query (nullptr = no tenant filter)
+  const int32_t* q_org = nullptr;
+  const int32_t* uniform = nullptr;      // host {user, org}: every query of the batch carries this scope
+  const int32_t* allow_rows = nullptr;   // device: rows that stay visible (subset search)
+  int64_t n_allow = -1;                  // -1 = no subset
+};
+
+// Enqueues one search over the published prefix `n_rows` on stream s using context c.
+int search_enqueue(aur_index* ix, SearchCtx* c, const void* q_dev, int nq, int k, const Scope& sc, int64_t n_rows,
+                   float* scores, int64_t* ids, double* scores64, cudaStream_t s,
+                   const FinalizeArgs::ExchangeOut* ex = nullptr) {
   if (nq <= 0 || k <= 0) return fail(AUR_ERR_INVALID, "nq and k must be positive");
   if (k > kMaxK) return fail(AUR_ERR_UNSUPPORTED, "k > %d", kMaxK);
   if (nq > 65535) return fail(AUR_ERR_UNSUPPORTED, "nq > 65535: split the batch");
-  const bool filtered = q_user != nullptr && uniform_scope == nullptr;   // per-query scopes: generic kernel only
+  const bool subset = sc.n_allow >= 0;
+  const bool filtered = sc.q_user != nullptr && sc.uniform == nullptr && !subset;   // per-query scopes: generic kernel only
   const int ksel = k + kSlack;
   int kernel = ix->opt_kernel;
   if (kernel == AUR_KERNEL_AUTO) kernel = tc_shape_ok(ix, k, filtered) ? AUR_KERNEL_TC2 : AUR_KERNEL_SIMT;
   if (kernel != AUR_KERNEL_SIMT && !tc_shape_ok(ix, k, filtered))
-    return fail(AUR_ERR_UNSUPPORTED, "tcgen05 path needs bf16, dim %% 64 == 0, dim <= %d, no tenant filter, and k small enough "
-                "for its shared-memory lists at this dim", kTcMaxDim);
-  ix->last_kernel = kernel;
-  ix->last_launches = 0;
-  CU_TRY(cudaEventRecord(ix->ev_begin, s));
+    return fail(AUR_ERR_UNSUPPORTED, "tcgen05 path needs bf16, dim %% 64 == 0, dim <= %d, no per-query tenant filter, and k small "
+                "enough for its shared-memory lists at this dim", kTcMaxDim);
+  c->last_kernel = kernel;
+  c->last_launches = 0;
+  c->snapshot_rows = n_rows;
+  CU_TRY(cudaEventRecord(c->ev_begin, s));
   bool k_timed = false;
-  const float* tc_inv = nullptr;
-  if (kernel != AUR_KERNEL_SIMT && q_user != nullptr && ix->rows > 0) {   // one scope for the whole batch
-    CU_TRY(ix->masked_inv.reserve(static_cast<size_t>(ix->capacity) + 64));
-    CU_TRY(launch_mask_inv_norm(ix->d_inv_norm, ix->d_user, ix->d_org, uniform_scope[0], uniform_scope[1], ix->rows,
-                                ix->masked_inv.p, s));
-    ++ix->last_launches;
-    tc_inv = ix->masked_inv.p;
+  const float* inv = nullptr;   // masked inverse norms (nullptr = the shard's own)
+  if (subset && n_rows > 0) {
+    CU_TRY(c->masked_inv.reserve(static_cast<size_t>(ix->capacity) + 64));
+    CU_TRY(launch_fill_f32(c->masked_inv.p, nanf(""), n_rows, s));
+    CU_TRY(launch_scatter_inv_norm(ix->d_inv_norm, sc.allow_rows, sc.n_allow, n_rows, c->masked_inv.p, s));
+    c->last_launches += 2;
+    inv = c->masked_inv.p;
+  } else if (kernel != AUR_KERNEL_SIMT && sc.q_user != nullptr && n_rows > 0) {   // one scope for the whole batch
+    CU_TRY(c->masked_inv.reserve(static_cast<size_t>(ix->capacity) + 64));
+    CU_TRY(launch_mask_inv_norm(ix->d_inv_norm, ix->d_user, ix->d_org, sc.uniform[0], sc.uniform[1], n_rows, c->masked_inv.p, s));
+    ++c->last_launches;
+    inv = c->masked_inv.p;
   }
 
   const int qstep = (kernel == AUR_KERNEL_SIMT) ? 1024 : 2 * kTcQRows;
@@ -239,35 +331,36 @@ int search_dev_locked(aur_index* ix, const void* q_dev, int nq, int k, const int
     int n_lists = 0;
     uint64_t* cur = nullptr;
     if (kernel == AUR_KERNEL_SIMT) {
-      if (ix->rows == 0) {
+      if (n_rows == 0) {
         n_lists = 1;
-        CU_TRY(ix->cand_a.reserve(static_cast<size_t>(nqb) * ksel));
-        CU_TRY(cudaMemsetAsync(ix->cand_a.p, 0, static_cast<size_t>(nqb) * ksel * 8, s));
+        CU_TRY(c->cand_a.reserve(static_cast<size_t>(nqb) * ksel));
+        CU_TRY(cudaMemsetAsync(c->cand_a.p, 0, static_cast<size_t>(nqb) * ksel * 8, s));
       } else {
-        n_lists = static_cast<int>((ix->rows + kSimtSeg - 1) / kSimtSeg);
-        CU_TRY(ix->cand_a.reserve(static_cast<size_t>(nqb) * n_lists * ksel));
+        n_lists = static_cast<int>((n_rows + kSimtSeg - 1) / kSimtSeg);
+        CU_TRY(c->cand_a.reserve(static_cast<size_t>(nqb) * n_lists * ksel));
         const int64_t chunk = 16 * kSimtSeg;  // 32768 rows of scores at a time
-        CU_TRY(ix->score_chunk.reserve(static_cast<size_t>(nqb) * chunk));
-        FilterArgs f{ix->d_user, ix->d_org, q_user ? q_user + q0 : nullptr, q_org ? q_org + q0 : nullptr};
-        if (!k_timed) CU_TRY(cudaEventRecord(ix->ev_k0, s));
-        for (int64_t r0 = 0; r0 < ix->rows; r0 += chunk) {
-          const int64_t nr = (ix->rows - r0 < chunk) ? ix->rows - r0 : chunk;
-          CU_TRY(launch_simt_scores(qb, ix->d_rows, ix->dtype, ix->dim, nqb, r0, nr, ix->rows, ix->d_inv_norm, f,
-                                    ix->score_chunk.p, s));
-          CU_TRY(launch_simt_select(ix->score_chunk.p, nqb, r0, nr, ksel, ix->cand_a.p, n_lists,
+        CU_TRY(c->score_chunk.reserve(static_cast<size_t>(nqb) * chunk));
+        FilterArgs f{ix->d_user, ix->d_org, nullptr, nullptr};
+        if (!subset && sc.q_user) { f.q_user = sc.q_user + q0; f.q_org = sc.q_org ? sc.q_org + q0 : nullptr; }
+        if (!k_timed) CU_TRY(cudaEventRecord(c->ev_k0, s));
+        for (int64_t r0 = 0; r0 < n_rows; r0 += chunk) {
+          const int64_t nr = (n_rows - r0 < chunk) ? n_rows - r0 : chunk;
+          CU_TRY(launch_simt_scores(qb, ix->d_rows, ix->dtype, ix->dim, nqb, r0, nr, n_rows, inv ? inv : ix->d_inv_norm, f,
+                                    c->score_chunk.p, s));
+          CU_TRY(launch_simt_select(c->score_chunk.p, nqb, r0, nr, ksel, c->cand_a.p, n_lists,
                                     static_cast<int>(r0 / kSimtSeg), s));
-          ix->last_launches += 2;
+          c->last_launches += 2;
         }
-        if (!k_timed) { CU_TRY(cudaEventRecord(ix->ev_k1, s)); k_timed = true; }
+        if (!k_timed) { CU_TRY(cudaEventRecord(c->ev_k1, s)); k_timed = true; }
       }
-      cur = ix->cand_a.p;
+      cur = c->cand_a.p;
     } else {
-      if (!k_timed) CU_TRY(cudaEventRecord(ix->ev_k0, s));
-      int rc = run_tc_block(ix, kernel == AUR_KERNEL_TC1 ? 1 : 2, qb, nqb, ksel, nullptr, &n_lists, s, tc_inv);
+      if (!k_timed) CU_TRY(cudaEventRecord(c->ev_k0, s));
+      int rc = run_tc_block(ix, c, kernel == AUR_KERNEL_TC1 ? 1 : 2, qb, nqb, ksel, n_rows, nullptr, &n_lists, s, inv);
       if (rc != AUR_OK) return rc;
-      if (!k_timed) { CU_TRY(cudaEventRecord(ix->ev_k1, s)); k_timed = true; }
-      ix->last_launches += 1;
-      cur = ix->cand_a.p;
+      if (!k_timed) { CU_TRY(cudaEventRecord(c->ev_k1, s)); k_timed = true; }
+      c->last_launches += 1;
+      cur = c->cand_a.p;
     }
     // dense candidate lists (SIMT path): fold until one sort of <= 4096 keys finishes the
     // job.  The tcgen05 kernel already compacted its survivors per query.
@@ -276,41 +369,47 @@ int search_dev_locked(aur_index* ix, const void* q_dev, int nq, int k, const int
     while (!compact && static_cast<int64_t>(n_lists) * ksel > 4096) {
       const int group = 4096 / ksel;
       const int n_groups = (n_lists + group - 1) / group;
-      DevBuf<uint64_t>& dst = in_a ? ix->cand_b : ix->cand_a;
+      DevBuf<uint64_t>& dst = in_a ? c->cand_b : c->cand_a;
       // rows of cand are indexed by the query position inside the block (TC pads to 128/256)
       CU_TRY(dst.reserve(static_cast<size_t>(nqb) * n_groups * ksel));
       CU_TRY(launch_reduce_lists(cur, nqb, n_lists, ksel, group, dst.p, s));
-      ix->last_launches += 1;
+      c->last_launches += 1;
       cur = dst.p; n_lists = n_groups; in_a = !in_a;
     }
-    FinalizeArgs fa;
+    FinalizeArgs fa{};
     fa.cand = cur; fa.n_lists = n_lists; fa.ksel = ksel;
-    fa.counts = compact ? ix->cand_count.p : nullptr;
+    fa.counts = compact ? c->cand_count.p : nullptr;
     fa.q = qb; fa.rows = ix->d_rows; fa.dtype = ix->dtype; fa.dim = ix->dim; fa.nq = nqb; fa.k = k;
     fa.ids = ix->d_ids;
-    fa.out_scores = scores + static_cast<size_t>(q0) * k;
-    fa.out_ids = ids + static_cast<size_t>(q0) * k;
+    fa.out_scores = scores ? scores + static_cast<size_t>(q0) * k : nullptr;
+    fa.out_ids = ids ? ids + static_cast<size_t>(q0) * k : nullptr;
     fa.out_scores64 = scores64 ? scores64 + static_cast<size_t>(q0) * k : nullptr;
+    if (ex) { fa.ex = *ex; fa.ex.q0 = q0; }
     CU_TRY(launch_finalize(fa, s));
-    ix->last_launches += 1;
+    c->last_launches += 1;
   }
-  if (!k_timed) { CU_TRY(cudaEventRecord(ix->ev_k0, s)); CU_TRY(cudaEventRecord(ix->ev_k1, s)); }
-  CU_TRY(cudaEventRecord(ix->ev_end, s));
-  ix->have_timing = true;
+  if (!k_timed) { CU_TRY(cudaEventRecord(c->ev_k0, s)); CU_TRY(cudaEventRecord(c->ev_k1, s)); }
+  CU_TRY(cudaEventRecord(c->ev_end, s));
+  c->have_timing = true;
+  {
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ix->last_ctx = c;
+  }
   return AUR_OK;
 }
 
+// Append n rows behind the published prefix and publish them once they have landed.  Caller holds mu_write.
 int add_common(aur_index* ix, const void* rows, bool rows_on_device, const int64_t* ids, const int32_t* users,
                const int32_t* orgs, int64_t n, cudaStream_t s) {
   if (n < 0) return fail(AUR_ERR_INVALID, "n < 0");
   if (n == 0) return AUR_OK;
   if (!rows || !ids) return fail(AUR_ERR_INVALID, "rows and ids are required");
-  if (ix->rows + n > ix->capacity)
-    return fail(AUR_ERR_NOMEM, "shard full: %lld + %lld > capacity %lld", (long long)ix->rows, (long long)n,
-                (long long)ix->capacity);
+  const int64_t base = ix->rows_pub.load(std::memory_order_relaxed);   // writers are serialised: nobody else moves it
+  if (base + n > ix->capacity)
+    return fail(AUR_ERR_NOMEM, "shard full: %lld + %lld > capacity %lld (aur_compact reclaims tombstones)", (long long)base,
+                (long long)n, (long long)ix->capacity);
   for (int64_t i = 0; i < n; ++i)
     if (ids[i] < 0) return fail(AUR_ERR_INVALID, "ids must be >= 0");
-  const int64_t base = ix->rows;
   uint8_t* dst = static_cast<uint8_t*>(ix->d_rows) + static_cast<size_t>(base) * ix->dim * ix->elt;
   CU_TRY(cudaMemcpyAsync(dst, rows, static_cast<size_t>(n) * ix->dim * ix->elt,
                          rows_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
@@ -322,17 +421,92 @@ int add_common(aur_index* ix, const void* rows, bool rows_on_device, const int64
   if (!orgs) { fill2.assign(static_cast<size_t>(n), -1); orgs = fill2.data(); }
   CU_TRY(cudaMemcpyAsync(ix->d_org + base, orgs, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, s));
   CU_TRY(launch_row_inv_norms(dst, ix->dtype, ix->dim, n, ix->d_inv_norm + base, s));
-  // upsert: an id that already exists loses its old row (weaviate_client.py:172 uuid5 semantics)
+  // upsert: an id that already exists loses its old row (weaviate_client.py:172 uuid5 semantics).  The old rows
+  // are tombstoned before the new ones are published: a racing search may briefly miss the object, never see it twice.
   std::vector<int64_t> dead;
-  for (int64_t i = 0; i < n; ++i) {
-    auto it = ix->id2row.find(ids[i]);
-    if (it != ix->id2row.end()) { dead.push_back(it->second); it->second = base + i; }
-    else { ix->id2row.emplace(ids[i], base + i); ++ix->live; }
+  {
+    std::lock_guard<std::mutex> lk(ix->mu);
+    for (int64_t i = 0; i < n; ++i) {
+      auto it = ix->id2row.find(ids[i]);
+      if (it != ix->id2row.end()) { dead.push_back(it->second); it->second = base + i; }
+      else { ix->id2row.emplace(ids[i], base + i); ++ix->live; }
+    }
   }
   const float nanv = nanf("");
   for (int64_t row : dead) CU_TRY(cudaMemcpyAsync(ix->d_inv_norm + row, &nanv, 4, cudaMemcpyHostToDevice, s));
-  ix->rows += n;
-  CU_TRY(cudaStreamSynchronize(s));  // host staging vectors go out of scope
+  CU_TRY(cudaStreamSynchronize(s));  // the data has landed (and the host staging vectors may go out of scope)
+  ix->rows_pub.store(base + n, std::memory_order_release);
+  return AUR_OK;
+}
+
+int check_search_args(aur_index* ix, const void* q, int32_t nq, int32_t k, const void* s_out, const void* i_out) {
+  if (!ix || !q || !s_out || !i_out) return fail(AUR_ERR_INVALID, "null argument");
+  if (nq <= 0 || k <= 0) return fail(AUR_ERR_INVALID, "nq and k must be positive");
+  return AUR_OK;
+}
+
+// Host-buffer search: H2D of the queries, kernels, D2H of the results on a pool context's own stream.
+int search_host(aur_index* ix, const void* queries_host, int32_t nq, int32_t k, const int32_t* q_user, const int32_t* q_org,
+                const int64_t* allow_ids, int64_t n_allow, float* scores_out, int64_t* ids_out, int64_t* snapshot_out) {
+  int rc = check_search_args(ix, queries_host, nq, k, scores_out, ids_out);
+  if (rc != AUR_OK) return rc;
+  std::shared_lock<std::shared_mutex> rl(ix->rw);
+  CU_TRY(cudaSetDevice(ix->device));
+  SearchCtx* c = nullptr;
+  if ((rc = acquire_ctx(ix, nullptr, &c)) != AUR_OK) return rc;
+  struct Guard { aur_index* ix; SearchCtx* c; ~Guard() { release_ctx(ix, c); } } guard{ix, c};
+  std::lock_guard<std::mutex> cl(c->mu);
+  cudaStream_t s = c->own_stream;
+  const int64_t n_rows = ix->rows_pub.load(std::memory_order_acquire);
+  const size_t qbytes = static_cast<size_t>(nq) * ix->dim * ix->elt;
+  const size_t nout = static_cast<size_t>(nq) * k;
+  CU_TRY(c->stage_q.reserve(qbytes));
+  CU_TRY(c->stage_scores.reserve(nout));
+  CU_TRY(c->stage_ids.reserve(nout));
+  CU_TRY(cudaMemcpyAsync(c->stage_q.p, queries_host, qbytes, cudaMemcpyHostToDevice, s));
+  Scope sc;
+  int32_t scope[2] = {0, -1};
+  std::vector<int32_t> rows_host;
+  if (allow_ids || n_allow > 0) {
+    // resolved metadata pre-filter: ids -> rows of the published prefix (unknown / newer ids drop out)
+    if (n_allow < 0 || (n_allow > 0 && !allow_ids)) return fail(AUR_ERR_INVALID, "allow_ids / n_allow");
+    rows_host.reserve(static_cast<size_t>(n_allow));
+    {
+      std::lock_guard<std::mutex> lk(ix->mu);
+      for (int64_t i = 0; i < n_allow; ++i) {
+        auto it = ix->id2row.find(allow_ids[i]);
+        if (it != ix->id2row.end() && it->second < n_rows) rows_host.push_back(static_cast<int32_t>(it->second));
+      }
+    }
+    CU_TRY(c->allow_rows.reserve(rows_host.size() + 1));
+    if (!rows_host.empty())
+      CU_TRY(cudaMemcpyAsync(c->allow_rows.p, rows_host.data(), rows_host.size() * 4, cudaMemcpyHostToDevice, s));
+    sc.allow_rows = c->allow_rows.p;
+    sc.n_allow = static_cast<int64_t>(rows_host.size());
+  } else if (q_user) {
+    CU_TRY(c->stage_quser.reserve(nq));
+    CU_TRY(cudaMemcpyAsync(c->stage_quser.p, q_user, static_cast<size_t>(nq) * 4, cudaMemcpyHostToDevice, s));
+    sc.q_user = c->stage_quser.p;
+    if (q_org) {
+      CU_TRY(c->stage_qorg.reserve(nq));
+      CU_TRY(cudaMemcpyAsync(c->stage_qorg.p, q_org, static_cast<size_t>(nq) * 4, cudaMemcpyHostToDevice, s));
+      sc.q_org = c->stage_qorg.p;
+    }
+    // the reference asks one tenant's question at a time (weaviate_client.py:244-249): when every query of the
+    // batch carries the same (user, org) scope the filter folds into the row scale and the tcgen05 kernel serves it
+    bool uniform = true;
+    scope[0] = q_user[0]; scope[1] = q_org ? q_org[0] : -1;
+    for (int i = 1; i < nq && uniform; ++i) uniform = q_user[i] == scope[0] && (q_org ? q_org[i] : -1) == scope[1];
+    if (uniform) sc.uniform = scope;
+  }
+  rc = search_enqueue(ix, c, c->stage_q.p, nq, k, sc, n_rows, c->stage_scores.p, c->stage_ids.p, nullptr, s);
+  if (rc != AUR_OK) { cudaStreamSynchronize(s); return rc; }
+  // straight into the caller's buffers (async when they are pinned); nothing is written
+  // unless every kernel above was enqueued successfully
+  CU_TRY(cudaMemcpyAsync(scores_out, c->stage_scores.p, nout * 4, cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaMemcpyAsync(ids_out, c->stage_ids.p, nout * 8, cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  if (snapshot_out) *snapshot_out = n_rows;
   return AUR_OK;
 }
 
@@ -372,9 +546,10 @@ int aur_open(const aur_config* cfg, aur_index** out) {
 #define OPEN_TRY(expr)                                                                                  \
   do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return bail(fail(e_ == cudaErrorMemoryAllocation ? AUR_ERR_NOMEM : AUR_ERR_CUDA, \
                                                                  "%s: %s", #expr, cudaGetErrorString(e_))); } while (0)
-  OPEN_TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
-  OPEN_TRY(cudaEventCreate(&ix->ev_begin)); OPEN_TRY(cudaEventCreate(&ix->ev_k0));
-  OPEN_TRY(cudaEventCreate(&ix->ev_k1));    OPEN_TRY(cudaEventCreate(&ix->ev_end));
+  int prio_lo = 0, prio_hi = 0;
+  OPEN_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  OPEN_TRY(cudaStreamCreateWithPriority(&ix->stream, cudaStreamNonBlocking, prio_hi));
+  OPEN_TRY(cudaStreamCreateWithPriority(&ix->ingest_stream, cudaStreamNonBlocking, prio_lo));
   // round the row store up to a whole tile so TMA boxes never straddle the allocation
   const int64_t cap_pad = (cfg->capacity + kTcTileN - 1) / kTcTileN * kTcTileN;
   OPEN_TRY(cudaMalloc(&ix->d_rows, static_cast<size_t>(cap_pad) * ix->dim * ix->elt));
@@ -392,32 +567,34 @@ int aur_open(const aur_config* cfg, aur_index** out) {
 int aur_close(aur_index* ix) {
   if (!ix) return AUR_OK;
   cudaSetDevice(ix->device);
-  if (ix->stream) cudaStreamSynchronize(ix->stream);
+  cudaDeviceSynchronize();   // searches bound to caller streams may still be in flight
   cudaFree(ix->d_rows); cudaFree(ix->d_inv_norm); cudaFree(ix->d_ids); cudaFree(ix->d_user); cudaFree(ix->d_org);
-  ix->cand_a.release(); ix->cand_b.release(); ix->pub.release(); ix->cand_count.release(); ix->score_chunk.release(); ix->masked_inv.release(); ix->stage_q.release();
-  ix->stage_quser.release(); ix->stage_qorg.release(); ix->stage_scores.release(); ix->stage_ids.release();
-  ix->dbg.release();
-  if (ix->ev_begin) cudaEventDestroy(ix->ev_begin);
-  if (ix->ev_k0) cudaEventDestroy(ix->ev_k0);
-  if (ix->ev_k1) cudaEventDestroy(ix->ev_k1);
-  if (ix->ev_end) cudaEventDestroy(ix->ev_end);
+  for (auto& c : ix->ctxs) c->release();
   if (ix->stream) cudaStreamDestroy(ix->stream);
+  if (ix->ingest_stream) cudaStreamDestroy(ix->ingest_stream);
   delete ix;
   return AUR_OK;
 }
 
 int aur_get_stats(aur_index* ix, aur_stats* out) {
   if (!ix || !out) return fail(AUR_ERR_INVALID, "null argument");
-  std::lock_guard<std::mutex> lk(ix->mu);
   memset(out, 0, sizeof *out);
-  out->rows = ix->rows; out->live = ix->live; out->capacity = ix->capacity;
-  out->dim = ix->dim; out->dtype = ix->dtype;
-  out->last_kernel = ix->last_kernel; out->last_launches = ix->last_launches;
-  if (ix->have_timing) {
-    CU_TRY(cudaSetDevice(ix->device));
-    CU_TRY(cudaEventSynchronize(ix->ev_end));
-    CU_TRY(cudaEventElapsedTime(&out->last_kernel_ms, ix->ev_k0, ix->ev_k1));
-    CU_TRY(cudaEventElapsedTime(&out->last_total_ms, ix->ev_begin, ix->ev_end));
+  SearchCtx* c = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(ix->mu);
+    out->rows = ix->rows_pub.load(std::memory_order_acquire); out->live = ix->live; out->capacity = ix->capacity;
+    out->dim = ix->dim; out->dtype = ix->dtype;
+    c = ix->last_ctx;
+  }
+  if (c) {
+    std::lock_guard<std::mutex> cl(c->mu);
+    out->last_kernel = c->last_kernel; out->last_launches = c->last_launches;
+    if (c->have_timing) {
+      CU_TRY(cudaSetDevice(ix->device));
+      CU_TRY(cudaEventSynchronize(c->ev_end));
+      CU_TRY(cudaEventElapsedTime(&out->last_kernel_ms, c->ev_k0, c->ev_k1));
+      CU_TRY(cudaEventElapsedTime(&out->last_total_ms, c->ev_begin, c->ev_end));
+    }
   }
   return AUR_OK;
 }
@@ -425,11 +602,12 @@ int aur_get_stats(aur_index* ix, aur_stats* out) {
 int aur_export(aur_index* ix, void* rows_out, int64_t* ids_out, int32_t* user_out, int32_t* org_out, uint8_t* live_out,
                int64_t n) {
   if (!ix || !rows_out || !ids_out || !live_out) return fail(AUR_ERR_INVALID, "null argument");
-  std::lock_guard<std::mutex> lk(ix->mu);
-  if (n != ix->rows) return fail(AUR_ERR_INVALID, "n must equal aur_stats.rows (%lld)", (long long)ix->rows);
+  std::unique_lock<std::shared_mutex> wl(ix->rw);
+  const int64_t rows = ix->rows_pub.load(std::memory_order_acquire);
+  if (n != rows) return fail(AUR_ERR_INVALID, "n must equal aur_stats.rows (%lld)", (long long)rows);
   if (n == 0) return AUR_OK;
   CU_TRY(cudaSetDevice(ix->device));
-  CU_TRY(cudaStreamSynchronize(ix->stream));
+  CU_TRY(cudaDeviceSynchronize());
   std::vector<float> inv(static_cast<size_t>(n));
   CU_TRY(cudaMemcpy(inv.data(), ix->d_inv_norm, sizeof(float) * n, cudaMemcpyDeviceToHost));
   CU_TRY(cudaMemcpy(rows_out, ix->d_rows, static_cast<size_t>(n) * ix->dim * ix->elt, cudaMemcpyDeviceToHost));
@@ -437,6 +615,65 @@ int aur_export(aur_index* ix, void* rows_out, int64_t* ids_out, int32_t* user_ou
   if (user_out) CU_TRY(cudaMemcpy(user_out, ix->d_user, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
   if (org_out) CU_TRY(cudaMemcpy(org_out, ix->d_org, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
   for (int64_t i = 0; i < n; ++i) live_out[i] = inv[static_cast<size_t>(i)] == inv[static_cast<size_t>(i)];   // NaN = tombstone
+  return AUR_OK;
+}
+
+int aur_compact(aur_index* ix, int64_t* reclaimed) {
+  if (!ix) return fail(AUR_ERR_INVALID, "null index");
+  if (reclaimed) *reclaimed = 0;
+  std::unique_lock<std::shared_mutex> wl(ix->rw);   // no search or append is being enqueued ...
+  std::lock_guard<std::mutex> wk(ix->mu_write);
+  CU_TRY(cudaSetDevice(ix->device));
+  CU_TRY(cudaDeviceSynchronize());                  // ... and none is still running
+  const int64_t rows = ix->rows_pub.load(std::memory_order_acquire);
+  std::vector<std::pair<int64_t, int64_t>> order;   // (old row, id) of the live rows, in row order
+  {
+    std::lock_guard<std::mutex> lk(ix->mu);
+    order.reserve(ix->id2row.size());
+    for (auto& kv : ix->id2row) order.emplace_back(kv.second, kv.first);
+  }
+  std::sort(order.begin(), order.end());
+  const int64_t nlive = static_cast<int64_t>(order.size());
+  if (nlive == rows) return AUR_OK;                 // nothing to reclaim
+  // Stable compaction in place, a bounce buffer at a time: live row j moves down to row j.  Chunk [i0, i1) only
+  // overwrites rows < i1 <= old(i1), i.e. rows whose content has already been gathered or moved.
+  const int64_t chunk = 65536;
+  DevBuf<int32_t> d_map; DevBuf<uint8_t> bounce; DevBuf<float> b_inv; DevBuf<int64_t> b_ids; DevBuf<int32_t> b_user, b_org;
+  cudaError_t e = d_map.reserve(static_cast<size_t>(chunk));
+  if (e == cudaSuccess) e = bounce.reserve(static_cast<size_t>(chunk) * ix->dim * ix->elt);
+  if (e == cudaSuccess) e = b_inv.reserve(chunk);
+  if (e == cudaSuccess) e = b_ids.reserve(chunk);
+  if (e == cudaSuccess) e = b_user.reserve(chunk);
+  if (e == cudaSuccess) e = b_org.reserve(chunk);
+  auto drop = [&]() { d_map.release(); bounce.release(); b_inv.release(); b_ids.release(); b_user.release(); b_org.release(); };
+  if (e != cudaSuccess) { drop(); return fail(AUR_ERR_NOMEM, "aur_compact: %s", cudaGetErrorString(e)); }
+  cudaStream_t s = ix->ingest_stream;
+  std::vector<int32_t> map_host(static_cast<size_t>(chunk));
+  int64_t first_moved = 0;
+  while (first_moved < nlive && order[static_cast<size_t>(first_moved)].first == first_moved) ++first_moved;   // untouched prefix
+  for (int64_t i0 = first_moved; i0 < nlive && e == cudaSuccess; i0 += chunk) {
+    const int64_t m = (nlive - i0 < chunk) ? nlive - i0 : chunk;
+    for (int64_t j = 0; j < m; ++j) map_host[static_cast<size_t>(j)] = static_cast<int32_t>(order[static_cast<size_t>(i0 + j)].first);
+    e = cudaMemcpyAsync(d_map.p, map_host.data(), static_cast<size_t>(m) * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = launch_gather_rows(ix->d_rows, ix->d_inv_norm, ix->d_ids, ix->d_user, ix->d_org, d_map.p, m,
+                                                 static_cast<int>(ix->dim * ix->elt), bounce.p, b_inv.p, b_ids.p, b_user.p, b_org.p, s);
+    const size_t rb = static_cast<size_t>(ix->dim) * ix->elt;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(static_cast<uint8_t*>(ix->d_rows) + static_cast<size_t>(i0) * rb, bounce.p, static_cast<size_t>(m) * rb, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ix->d_inv_norm + i0, b_inv.p, static_cast<size_t>(m) * 4, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ix->d_ids + i0, b_ids.p, static_cast<size_t>(m) * 8, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ix->d_user + i0, b_user.p, static_cast<size_t>(m) * 4, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ix->d_org + i0, b_org.p, static_cast<size_t>(m) * 4, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);   // map_host is reused by the next chunk
+  }
+  drop();
+  if (e != cudaSuccess) return fail(AUR_ERR_CUDA, "aur_compact: %s (the shard may be inconsistent: restore the last snapshot)", cudaGetErrorString(e));
+  {
+    std::lock_guard<std::mutex> lk(ix->mu);
+    for (int64_t j = 0; j < nlive; ++j) ix->id2row[order[static_cast<size_t>(j)].second] = j;
+    ix->live = nlive;
+  }
+  ix->rows_pub.store(nlive, std::memory_order_release);
+  if (reclaimed) *reclaimed = rows - nlive;
   return AUR_OK;
 }
 
@@ -467,89 +704,93 @@ int aur_sync(aur_index* ix) {
 int aur_add(aur_index* ix, const void* rows_host, const int64_t* ids, const int32_t* user_codes,
             const int32_t* org_codes, int64_t n) {
   if (!ix) return fail(AUR_ERR_INVALID, "null index");
-  std::lock_guard<std::mutex> lk(ix->mu);
+  std::shared_lock<std::shared_mutex> rl(ix->rw);
+  std::lock_guard<std::mutex> wk(ix->mu_write);
   CU_TRY(cudaSetDevice(ix->device));
-  return add_common(ix, rows_host, false, ids, user_codes, org_codes, n, ix->stream);
+  return add_common(ix, rows_host, false, ids, user_codes, org_codes, n, ix->ingest_stream);
 }
 
 int aur_add_dev(aur_index* ix, const void* rows_dev, const int64_t* ids_host, const int32_t* user_codes_host,
                 const int32_t* org_codes_host, int64_t n, void* stream) {
   if (!ix) return fail(AUR_ERR_INVALID, "null index");
-  std::lock_guard<std::mutex> lk(ix->mu);
+  std::shared_lock<std::shared_mutex> rl(ix->rw);
+  std::lock_guard<std::mutex> wk(ix->mu_write);
   CU_TRY(cudaSetDevice(ix->device));
   return add_common(ix, rows_dev, true, ids_host, user_codes_host, org_codes_host, n,
-                    stream ? static_cast<cudaStream_t>(stream) : ix->stream);
+                    stream ? static_cast<cudaStream_t>(stream) : ix->ingest_stream);
 }
 
 int aur_remove(aur_index* ix, const int64_t* ids, int64_t n, int64_t* removed) {
   if (!ix || (n > 0 && !ids)) return fail(AUR_ERR_INVALID, "null argument");
-  std::lock_guard<std::mutex> lk(ix->mu);
+  std::shared_lock<std::shared_mutex> rl(ix->rw);
+  std::lock_guard<std::mutex> wk(ix->mu_write);
   CU_TRY(cudaSetDevice(ix->device));
   const float nanv = nanf("");
-  int64_t cnt = 0;
-  for (int64_t i = 0; i < n; ++i) {
-    auto it = ix->id2row.find(ids[i]);
-    if (it == ix->id2row.end()) continue;
-    CU_TRY(cudaMemcpyAsync(ix->d_inv_norm + it->second, &nanv, 4, cudaMemcpyHostToDevice, ix->stream));
-    ix->id2row.erase(it);
-    --ix->live; ++cnt;
+  std::vector<int64_t> dead;
+  {
+    std::lock_guard<std::mutex> lk(ix->mu);
+    for (int64_t i = 0; i < n; ++i) {
+      auto it = ix->id2row.find(ids[i]);
+      if (it == ix->id2row.end()) continue;
+      dead.push_back(it->second);
+      ix->id2row.erase(it);
+      --ix->live;
+    }
   }
-  CU_TRY(cudaStreamSynchronize(ix->stream));
-  if (removed) *removed = cnt;
+  for (int64_t row : dead) CU_TRY(cudaMemcpyAsync(ix->d_inv_norm + row, &nanv, 4, cudaMemcpyHostToDevice, ix->ingest_stream));
+  CU_TRY(cudaStreamSynchronize(ix->ingest_stream));
+  if (removed) *removed = static_cast<int64_t>(dead.size());
   return AUR_OK;
 }
 
 int aur_search_dev(aur_index* ix, const void* queries_dev, int32_t nq, int32_t k, const int32_t* q_user_dev,
                    const int32_t* q_org_dev, float* scores_dev, int64_t* ids_dev, double* scores64_dev, void* stream) {
-  if (!ix || !queries_dev || !scores_dev || !ids_dev) return fail(AUR_ERR_INVALID, "null argument");
-  std::lock_guard<std::mutex> lk(ix->mu);
+  int rc = check_search_args(ix, queries_dev, nq, k, scores_dev, ids_dev);
+  if (rc != AUR_OK) return rc;
+  std::shared_lock<std::shared_mutex> rl(ix->rw);
   CU_TRY(cudaSetDevice(ix->device));
-  return search_dev_locked(ix, queries_dev, nq, k, q_user_dev, q_org_dev, scores_dev, ids_dev, scores64_dev,
-                           stream ? static_cast<cudaStream_t>(stream) : ix->stream);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ix->stream;
+  SearchCtx* c = nullptr;
+  if ((rc = acquire_ctx(ix, s, &c)) != AUR_OK) return rc;
+  std::lock_guard<std::mutex> cl(c->mu);
+  Scope sc;
+  sc.q_user = q_user_dev; sc.q_org = q_org_dev;
+  return search_enqueue(ix, c, queries_dev, nq, k, sc, ix->rows_pub.load(std::memory_order_acquire), scores_dev, ids_dev,
+                        scores64_dev, s);
 }
 
 int aur_search(aur_index* ix, const void* queries_host, int32_t nq, int32_t k, const int32_t* q_user,
                const int32_t* q_org, float* scores_out, int64_t* ids_out) {
-  if (!ix || !queries_host || !scores_out || !ids_out) return fail(AUR_ERR_INVALID, "null argument");
-  if (nq <= 0 || k <= 0) return fail(AUR_ERR_INVALID, "nq and k must be positive");
-  std::lock_guard<std::mutex> lk(ix->mu);
-  CU_TRY(cudaSetDevice(ix->device));
-  cudaStream_t s = ix->stream;
-  const size_t qbytes = static_cast<size_t>(nq) * ix->dim * ix->elt;
-  const size_t nout = static_cast<size_t>(nq) * k;
-  CU_TRY(ix->stage_q.reserve(qbytes));
-  CU_TRY(ix->stage_scores.reserve(nout));
-  CU_TRY(ix->stage_ids.reserve(nout));
-  CU_TRY(cudaMemcpyAsync(ix->stage_q.p, queries_host, qbytes, cudaMemcpyHostToDevice, s));
-  const int32_t* du = nullptr; const int32_t* dorg = nullptr;
-  if (q_user) {
-    CU_TRY(ix->stage_quser.reserve(nq));
-    CU_TRY(cudaMemcpyAsync(ix->stage_quser.p, q_user, static_cast<size_t>(nq) * 4, cudaMemcpyHostToDevice, s));
-    du = ix->stage_quser.p;
-    if (q_org) {
-      CU_TRY(ix->stage_qorg.reserve(nq));
-      CU_TRY(cudaMemcpyAsync(ix->stage_qorg.p, q_org, static_cast<size_t>(nq) * 4, cudaMemcpyHostToDevice, s));
-      dorg = ix->stage_qorg.p;
-    }
-  }
-  // the reference asks one tenant's question at a time (weaviate_client.py:244-249): when every query of the
-  // batch carries the same (user, org) scope the filter folds into the row scale and the tcgen05 kernel serves it
-  int32_t scope[2] = {0, -1};
-  bool uniform = q_user != nullptr;
-  if (uniform) {
-    scope[0] = q_user[0]; scope[1] = q_org ? q_org[0] : -1;
-    for (int i = 1; i < nq && uniform; ++i) uniform = q_user[i] == scope[0] && (q_org ? q_org[i] : -1) == scope[1];
-  }
-  int rc = search_dev_locked(ix, ix->stage_q.p, nq, k, du, dorg, ix->stage_scores.p, ix->stage_ids.p, nullptr, s,
-                             uniform ? scope : nullptr);
-  if (rc != AUR_OK) return rc;
-  // straight into the caller's buffers (async when they are pinned); nothing is written
-  // unless every kernel above was enqueued successfully
-  CU_TRY(cudaMemcpyAsync(scores_out, ix->stage_scores.p, nout * 4, cudaMemcpyDeviceToHost, s));
-  CU_TRY(cudaMemcpyAsync(ids_out, ix->stage_ids.p, nout * 8, cudaMemcpyDeviceToHost, s));
-  CU_TRY(cudaStreamSynchronize(s));
-  return AUR_OK;
+  return search_host(ix, queries_host, nq, k, q_user, q_org, nullptr, -1, scores_out, ids_out, nullptr);
 }
+
+int aur_search_ex(aur_index* ix, const void* queries_host, int32_t nq, int32_t k, const int32_t* q_user,
+                  const int32_t* q_org, float* scores_out, int64_t* ids_out, int64_t* snapshot_rows_out) {
+  return search_host(ix, queries_host, nq, k, q_user, q_org, nullptr, -1, scores_out, ids_out, snapshot_rows_out);
+}
+
+int aur_search_subset(aur_index* ix, const void* queries_host, int32_t nq, int32_t k, const int64_t* allow_ids,
+                      int64_t n_allow, float* scores_out, int64_t* ids_out) {
+  if (n_allow < 0) return fail(AUR_ERR_INVALID, "n_allow < 0");
+  static const int64_t none = 0;
+  return search_host(ix, queries_host, nq, k, nullptr, nullptr, allow_ids ? allow_ids : &none, n_allow, scores_out, ids_out, nullptr);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused cross-shard exchange (row-sharded corpus, one process per GPU).  Each rank owns one buffer in its HBM that
+// every other rank maps through CUDA IPC; a shard's exact top-k rows are stored into all buffers by the finalize
+// kernel itself and a flag per (parity, source rank) says when a slot is complete.  No NCCL call, no host
+// round trip: local search -> peer stores -> merge is three kernels on one stream.
+struct aur_exchange {
+  int device = 0, rank = 0, world = 1, nq_max = 0, k_max = 0;
+  size_t plane = 0, slot_stride = 0, parity_stride = 0, flags_off = 0, bytes = 0;   // in 8-byte words (bytes: bytes)
+  uint64_t* local = nullptr;           // this rank's buffer (cudaMalloc, exported through cudaIpc)
+  uint64_t* peer[8] = {};              // every rank's buffer as mapped here (peer[rank] == local)
+  uint64_t* d_seq = nullptr;           // exchanges completed
+  uint32_t* d_done = nullptr;          // merge kernel's block counter, then the status word
+  bool connected = false;
+};
 
 int aur_merge_topk_dev(int32_t device, const double* in_scores64, const int64_t* in_ids, int32_t n_shards, int32_t nq,
                        int32_t k, float* out_scores, int64_t* out_ids, double* out_scores64, void* stream) {
@@ -573,6 +814,116 @@ int aur_merge_topk_packed_dev(int32_t device, const void* packed, int32_t n_shar
   const int64_t* ids = static_cast<const int64_t*>(packed) + plane;
   CU_TRY(launch_merge_topk(s64, ids, 2 * plane, n_shards, nq, k, out_scores, out_ids, out_scores64,
                            static_cast<cudaStream_t>(stream)));
+  return AUR_OK;
+}
+
+int aur_exchange_create(int32_t device, int32_t rank, int32_t world, int32_t nq_max, int32_t k_max, aur_exchange** out,
+                        uint8_t* handle_out /* [64] */) {
+  if (!out || !handle_out) return fail(AUR_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(AUR_ERR_INVALID, "1 <= world <= 8, 0 <= rank < world");
+  if (nq_max <= 0 || k_max <= 0 || k_max > kMaxK || world * k_max > 2048) return fail(AUR_ERR_INVALID, "bad nq_max / k_max");
+  if (aur_device_count() == 0) return fail(AUR_ERR_NO_DEVICE, "no CUDA device");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  CU_TRY(cudaSetDevice(device));
+  aur_exchange* ex = new aur_exchange();
+  ex->device = device; ex->rank = rank; ex->world = world; ex->nq_max = nq_max; ex->k_max = k_max;
+  ex->plane = static_cast<size_t>(nq_max) * k_max;
+  ex->slot_stride = 2 * ex->plane;
+  ex->parity_stride = static_cast<size_t>(world) * ex->slot_stride;
+  ex->flags_off = 2 * ex->parity_stride;
+  ex->bytes = (ex->flags_off + 2 * static_cast<size_t>(world) + 16) * 8;
+  cudaError_t e = cudaMalloc(&ex->local, ex->bytes);
+  if (e == cudaSuccess) e = cudaMemset(ex->local, 0, ex->bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&ex->d_seq, 8);
+  if (e == cudaSuccess) e = cudaMemset(ex->d_seq, 0, 8);
+  if (e == cudaSuccess) e = cudaMalloc(&ex->d_done, 8);
+  if (e == cudaSuccess) e = cudaMemset(ex->d_done, 0, 8);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess && world > 1) e = cudaIpcGetMemHandle(&h, ex->local);
+  if (e != cudaSuccess) {
+    cudaFree(ex->local); cudaFree(ex->d_seq); cudaFree(ex->d_done); delete ex;
+    return fail(AUR_ERR_CUDA, "aur_exchange_create: %s", cudaGetErrorString(e));
+  }
+  if (world > 1) memcpy(handle_out, &h, 64); else memset(handle_out, 0, 64);
+  ex->peer[rank] = ex->local;
+  ex->connected = world == 1;
+  *out = ex;
+  return AUR_OK;
+}
+
+int aur_exchange_connect(aur_exchange* ex, const uint8_t* all_handles /* [world][64], rank order */) {
+  if (!ex || !all_handles) return fail(AUR_ERR_INVALID, "null argument");
+  CU_TRY(cudaSetDevice(ex->device));
+  for (int r = 0; r < ex->world; ++r) {
+    if (r == ex->rank || ex->peer[r]) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, all_handles + static_cast<size_t>(r) * 64, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(AUR_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+    ex->peer[r] = static_cast<uint64_t*>(p);
+  }
+  ex->connected = true;
+  return AUR_OK;
+}
+
+int aur_exchange_close(aur_exchange* ex) {
+  if (!ex) return AUR_OK;
+  cudaSetDevice(ex->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < ex->world; ++r)
+    if (r != ex->rank && ex->peer[r]) cudaIpcCloseMemHandle(ex->peer[r]);
+  cudaFree(ex->local); cudaFree(ex->d_seq); cudaFree(ex->d_done);
+  delete ex;
+  return AUR_OK;
+}
+
+int aur_exchange_status(aur_exchange* ex, int64_t* exchanges_done, int32_t* status) {
+  if (!ex) return fail(AUR_ERR_INVALID, "null argument");
+  CU_TRY(cudaSetDevice(ex->device));
+  uint64_t seq = 0; uint32_t st[2] = {0, 0};
+  CU_TRY(cudaMemcpy(&seq, ex->d_seq, 8, cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(st, ex->d_done, 8, cudaMemcpyDeviceToHost));
+  if (exchanges_done) *exchanges_done = static_cast<int64_t>(seq);
+  if (status) *status = static_cast<int32_t>(st[1]);
+  return AUR_OK;
+}
+
+int aur_search_exchange_dev(aur_index* ix, aur_exchange* ex, const void* queries_dev, int32_t nq, int32_t k,
+                            float* scores_dev, int64_t* ids_dev, void* stream) {
+  int rc = check_search_args(ix, queries_dev, nq, k, scores_dev, ids_dev);
+  if (rc != AUR_OK) return rc;
+  if (!ex || !ex->connected) return fail(AUR_ERR_INVALID, "exchange not connected");
+  if (ex->device != ix->device) return fail(AUR_ERR_INVALID, "exchange and index live on different devices");
+  if (nq > ex->nq_max || k > ex->k_max || static_cast<size_t>(nq) * k > ex->plane)
+    return fail(AUR_ERR_INVALID, "batch %d x top-%d exceeds the exchange's %d x %d", nq, k, ex->nq_max, ex->k_max);
+  std::shared_lock<std::shared_mutex> rl(ix->rw);
+  CU_TRY(cudaSetDevice(ix->device));
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ix->stream;
+  SearchCtx* c = nullptr;
+  if ((rc = acquire_ctx(ix, s, &c)) != AUR_OK) return rc;
+  std::lock_guard<std::mutex> cl(c->mu);
+  FinalizeArgs::ExchangeOut eo{};
+  eo.n_peers = ex->world;
+  for (int r = 0; r < ex->world; ++r) eo.slot[r] = ex->peer[r] + static_cast<size_t>(ex->rank) * ex->slot_stride;
+  eo.seq = ex->d_seq;
+  eo.parity_stride = ex->parity_stride;
+  eo.plane_stride = ex->plane;
+  Scope sc;
+  rc = search_enqueue(ix, c, queries_dev, nq, k, sc, ix->rows_pub.load(std::memory_order_acquire), nullptr, nullptr, nullptr, s, &eo);
+  if (rc != AUR_OK) return rc;
+  ExchangeParams p{};
+  p.slots = ex->local; p.flags = ex->local + ex->flags_off;
+  for (int r = 0; r < ex->world; ++r) p.peer_flags[r] = ex->peer[r] + ex->flags_off;
+  p.seq = ex->d_seq; p.done = ex->d_done; p.status = ex->d_done + 1;
+  p.world = ex->world; p.rank = ex->rank; p.nq = nq; p.k = k;
+  p.parity_stride = ex->parity_stride; p.slot_stride = ex->slot_stride; p.plane_stride = ex->plane;
+  p.out_scores = scores_dev; p.out_ids = ids_dev;
+  CU_TRY(launch_exchange_merge(p, s));
+  c->last_launches += 1;
+  CU_TRY(cudaEventRecord(c->ev_end, s));
   return AUR_OK;
 }
 
@@ -636,15 +987,20 @@ int aur_memcpy_d2h(int32_t device, void* dst_host, const void* src_dev, uint64_t
 int aur_debug_tc_scores(aur_index* ix, const void* queries_dev, int32_t nq, int32_t cta_group, float* out_dev,
                         int32_t* n_ctas_out, void* stream) {
   if (!ix || !queries_dev || !out_dev) return fail(AUR_ERR_INVALID, "null argument");
-  std::lock_guard<std::mutex> lk(ix->mu);
+  std::shared_lock<std::shared_mutex> rl(ix->rw);
   CU_TRY(cudaSetDevice(ix->device));
   if (!ix->tmap_ok) return fail(AUR_ERR_UNSUPPORTED, "index shape has no tcgen05 path");
   if (nq <= 0 || nq > 2 * kTcQRows) return fail(AUR_ERR_INVALID, "1..256 queries");
   int n_lists = 0;
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ix->stream;
-  int rc = run_tc_block(ix, cta_group, queries_dev, nq, 32 + kSlack, out_dev, &n_lists, s);
+  SearchCtx* c = nullptr;
+  int rc = acquire_ctx(ix, s, &c);
   if (rc != AUR_OK) return rc;
-  CU_TRY(cudaMemsetAsync(ix->cand_count.p, 0, 2 * kTcQRows * 4, s));  // no finalize ran to reset them
+  std::lock_guard<std::mutex> cl(c->mu);
+  rc = run_tc_block(ix, c, cta_group, queries_dev, nq, 32 + kSlack, ix->rows_pub.load(std::memory_order_acquire), out_dev,
+                    &n_lists, s);
+  if (rc != AUR_OK) return rc;
+  CU_TRY(cudaMemsetAsync(c->cand_count.p, 0, 2 * kTcQRows * 4, s));  // no finalize ran to reset them
   if (n_ctas_out) *n_ctas_out = ix->sm_count & ~1;
   return AUR_OK;
 }

@@ -62,7 +62,10 @@ struct TcParams {
   int64_t n_rows;
   uint32_t epoch;           // launch counter: pub entries of older launches are ignored
   int nq, dim, ksel, n_lists, n_qblocks, num_stages, n_tiles;
-  int dbg_flags;            // bring-up only: 1 = epilogue skips its work, 2 = no MMAs issued
+  int dbg_flags;            // bring-up only (timing decomposition; results are wrong with 1..32): 1 = epilogue neither
+                            // reads nor examines the accumulator, 2 = no MMAs issued, 4 = accumulator read but not
+                            // examined, 8 = scaled + maxima but no threshold test, 16 = no per-tile threshold read,
+                            // 32 = no inverse-norm prefetch, 64 = per-thread counters into dbg_scores
 };
 constexpr int kTcPubMax = 74;      // published values a thread folds into its threshold
 
@@ -102,9 +105,32 @@ struct FinalizeArgs {
                      // (reset to 0 by the kernel); null = all n_lists * ksel slots are keys
   const void* q; const void* rows; int dtype; int dim; int nq; int k;
   const int64_t* ids;
-  float* out_scores; int64_t* out_ids; double* out_scores64;
+  float* out_scores; int64_t* out_ids; double* out_scores64;   // (out_scores / out_ids nullable in exchange mode)
   int sort_cap;      // set by launch_finalize: keys the shared sort buffer holds
+  // Fused cross-shard exchange (ExchangeOut.n_peers > 0): the exact (fp64 score, id) rows of this shard are
+  // stored straight into every rank's exchange buffer over NVLink instead of a local array + all-gather.
+  struct ExchangeOut {
+    uint64_t* slot[8];          // per destination rank: base of THIS rank's slot in that rank's buffer (parity 0)
+    int n_peers;                // 0 = off
+    const uint64_t* seq;        // device word: exchanges completed so far (this one is *seq + 1; parity = its low bit)
+    size_t parity_stride;       // 8-byte words between the two parities of a buffer
+    size_t plane_stride;        // words between the score plane and the id plane of a slot
+    int q0;                     // first query of this launch inside the batch
+  } ex;
 };
+// Cross-shard merge fed by the peer stores above: signal every peer, wait for all of them, keep the best k.
+struct ExchangeParams {
+  uint64_t* slots;              // this rank's buffer: [2 parity][world][2 planes][plane_stride]
+  uint64_t* flags;              // this rank's flags:  [2 parity][world]   (sequence number a peer has delivered)
+  uint64_t* peer_flags[8];      // the same array in every rank's buffer
+  uint64_t* seq;                // device word, bumped by the last block
+  uint32_t* done;               // block counter (self-resetting)
+  uint32_t* status;             // != 0: a peer did not deliver in time
+  int world, rank, nq, k;
+  size_t parity_stride, slot_stride, plane_stride;
+  float* out_scores; int64_t* out_ids;
+};
+cudaError_t launch_exchange_merge(const ExchangeParams& p, cudaStream_t s);
 cudaError_t launch_finalize(const FinalizeArgs& a, cudaStream_t s);
 // shard_stride: elements between consecutive shards' blocks in in_s / in_ids
 cudaError_t launch_merge_topk(const double* in_s, const int64_t* in_ids, size_t shard_stride, int n_shards, int nq, int k,
@@ -116,6 +142,13 @@ cudaError_t launch_fill_f32(float* p, float v, int64_t n, cudaStream_t s);
 // carry the same tenant scope
 cudaError_t launch_mask_inv_norm(const float* inv, const int32_t* row_user, const int32_t* row_org, int32_t u, int32_t o,
                                  int64_t n, float* out, cudaStream_t s);
+
+// out[rows[i]] = inv[rows[i]] for the listed rows (out pre-filled with NaN): a resolved id subset as a row mask
+cudaError_t launch_scatter_inv_norm(const float* inv, const int32_t* rows, int64_t n, int64_t n_rows, float* out, cudaStream_t s);
+// compaction: rows map[0..n) (and their side arrays) -> bounce buffers
+cudaError_t launch_gather_rows(const void* rows, const float* inv, const int64_t* ids, const int32_t* user, const int32_t* org,
+                               const int32_t* map, int64_t n, int row_bytes, void* o_rows, float* o_inv, int64_t* o_ids,
+                               int32_t* o_user, int32_t* o_org, cudaStream_t s);
 
 // ---------------------------------------------------------------- encoder (BERT-family forward)
 // out = epi(A . W^T + bias): A [m_tiles*128, K] bf16 (TMA box {64,128}), W [N, K] bf16 (TMA box {64,BN}).

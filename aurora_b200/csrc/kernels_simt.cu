@@ -283,6 +283,22 @@ finalize_kernel(FinalizeArgs a) {
     }
   }
   __syncthreads();
+  // where a result row goes: local arrays and / or this rank's slot in every rank's exchange buffer (peer stores)
+  const uint64_t ex_par = (a.ex.n_peers > 0) ? (((*a.ex.seq + 1) & 1ull) * a.ex.parity_stride) : 0ull;
+  auto emit = [&](int pos, double s, int64_t id) {
+    const size_t o = static_cast<size_t>(qi) * a.k + pos;
+    if (a.out_scores) { a.out_scores[o] = static_cast<float>(s); a.out_ids[o] = id; }
+    if (a.out_scores64) a.out_scores64[o] = s;
+    if (a.ex.n_peers > 0) {
+      const size_t w = ex_par + static_cast<size_t>(a.ex.q0 + qi) * a.k + pos;
+      const uint64_t sb = static_cast<uint64_t>(__double_as_longlong(s));
+#pragma unroll 1
+      for (int r = 0; r < a.ex.n_peers; ++r) {
+        a.ex.slot[r][w] = sb;
+        a.ex.slot[r][w + a.ex.plane_stride] = static_cast<uint64_t>(id);
+      }
+    }
+  };
   // rank by counting: ids are unique, so (score desc, id asc) is a total order
   for (int t = threadIdx.x; t < ncand; t += blockDim.x) {
     const double s = ex_score[t]; const int64_t id = ex_id[t];
@@ -292,20 +308,12 @@ finalize_kernel(FinalizeArgs a) {
       const double su = ex_score[u]; const int64_t iu = ex_id[u];
       if (iu >= 0 && (su > s || (su == s && iu < id))) ++rank;
     }
-    if (rank < a.k) {
-      const size_t o = static_cast<size_t>(qi) * a.k + rank;
-      a.out_scores[o] = static_cast<float>(s); a.out_ids[o] = id;
-      if (a.out_scores64) a.out_scores64[o] = s;
-    }
+    if (rank < a.k) emit(rank, s, id);
   }
   __shared__ int s_nvalid;
   if (threadIdx.x == 0) { int nv = 0; for (int u = 0; u < ncand; ++u) nv += ex_id[u] >= 0; s_nvalid = nv; }
   __syncthreads();
-  for (int t = s_nvalid + threadIdx.x; t < a.k; t += blockDim.x) {
-    const size_t o = static_cast<size_t>(qi) * a.k + t;
-    a.out_scores[o] = -INFINITY; a.out_ids[o] = -1;
-    if (a.out_scores64) a.out_scores64[o] = -INFINITY;
-  }
+  for (int t = s_nvalid + threadIdx.x; t < a.k; t += blockDim.x) emit(t, -INFINITY, -1);
 }
 
 // Cross-shard merge of exact (fp64 score, id) lists: [n_shards, nq, k] -> [nq, k].
@@ -346,6 +354,81 @@ merge_topk_kernel(const double* __restrict__ in_s, const int64_t* __restrict__ i
     const size_t o = static_cast<size_t>(qi) * k + t;
     out_s[o] = -INFINITY; out_ids[o] = -1;
     if (out_s64) out_s64[o] = -INFINITY;
+  }
+}
+
+// Fused exchange, receiving side.  Every rank's finalize kernels have stored their (fp64 score, id) rows into
+// slot [parity][rank] of EVERY rank's buffer (plain peer stores over NVLink).  This kernel, next in the stream:
+//   1. block 0 publishes "rank r delivered exchange #seq" into every rank's flag array (release at system scope:
+//      the finalize kernels' stores happen-before it by stream order);
+//   2. every block waits until all `world` flags of this rank show seq (acquire), i.e. all slots are complete;
+//   3. block q merges query q's world x k candidates by (score desc, id asc);
+//   4. the last block to finish bumps the sequence word, so a replayed CUDA graph advances by itself.
+// Two parities: rank A can only write exchange s+2 after its own merge s+1, which waited for B's delivery s+1,
+// which B issued after finishing its merge s -- so a slot is never overwritten while someone still reads it.
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+  uint64_t v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+exchange_merge_kernel(ExchangeParams p) {
+  extern __shared__ uint8_t sm[];
+  double* sc = reinterpret_cast<double*>(sm);
+  int64_t* id = reinterpret_cast<int64_t*>(sc + p.world * p.k);
+  __shared__ int s_nvalid;
+  const uint64_t seq = *p.seq + 1;
+  const size_t par = (seq & 1ull) * p.parity_stride;
+  const int qi = blockIdx.x, n = p.world * p.k;
+  if (blockIdx.x == 0 && threadIdx.x < p.world) {
+    __threadfence_system();
+    st_release_sys(p.peer_flags[threadIdx.x] + (seq & 1ull) * p.world + p.rank, seq);
+  }
+  if (threadIdx.x < p.world) {
+    const uint64_t* f = p.flags + (seq & 1ull) * p.world + threadIdx.x;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(f) < seq) {
+      __nanosleep(40);
+      if (clock64() - t0 > 4000000000ll) { atomicExch(p.status, 1u + threadIdx.x); break; }   // ~2 s: a peer died
+    }
+  }
+  if (threadIdx.x == 0) s_nvalid = 0;
+  __syncthreads();
+  const uint64_t* base = p.slots + par;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int sh = i / p.k, t = i % p.k;
+    const uint64_t* slot = base + static_cast<size_t>(sh) * p.slot_stride + static_cast<size_t>(qi) * p.k + t;
+    sc[i] = __longlong_as_double(static_cast<long long>(__ldcv(slot)));
+    id[i] = static_cast<int64_t>(__ldcv(slot + p.plane_stride));
+  }
+  __syncthreads();
+  int local_valid = 0;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    const double s = sc[t]; const int64_t me = id[t];
+    if (me < 0) continue;
+    ++local_valid;
+    int rank = 0;
+    for (int u = 0; u < n; ++u) {
+      const double su = sc[u]; const int64_t iu = id[u];
+      if (iu >= 0 && (su > s || (su == s && iu < me))) ++rank;
+    }
+    if (rank < p.k) {
+      const size_t o = static_cast<size_t>(qi) * p.k + rank;
+      p.out_scores[o] = static_cast<float>(s); p.out_ids[o] = me;
+    }
+  }
+  atomicAdd(&s_nvalid, local_valid);
+  __syncthreads();
+  for (int t = s_nvalid + threadIdx.x; t < p.k; t += blockDim.x) {
+    const size_t o = static_cast<size_t>(qi) * p.k + t;
+    p.out_scores[o] = -INFINITY; p.out_ids[o] = -1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(p.done, 1u) == gridDim.x - 1) { *p.done = 0; __threadfence(); *p.seq = seq; }
   }
 }
 
@@ -448,6 +531,13 @@ cudaError_t launch_merge_topk(const double* in_s, const int64_t* in_ids, size_t 
   return cudaGetLastError();
 }
 
+cudaError_t launch_exchange_merge(const ExchangeParams& p, cudaStream_t s) {
+  const size_t smem = static_cast<size_t>(p.world) * p.k * 16;
+  if (smem > 48 * 1024 || p.world > 8) return cudaErrorInvalidValue;
+  exchange_merge_kernel<<<p.nq, 256, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_cosine_pairs(const float* a, const float* b, int64_t n, int dim, int clamp, double* out,
                                 cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
@@ -473,6 +563,51 @@ cudaError_t launch_mask_inv_norm(const float* inv, const int32_t* row_user, cons
                                  int64_t n, float* out, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
   mask_inv_norm_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(inv, row_user, row_org, u, o, n, out);
+  return cudaGetLastError();
+}
+
+// Subset search: out was filled with NaN; the listed rows get their inverse norm back (a tombstone stays NaN).
+__global__ void scatter_inv_norm_kernel(const float* __restrict__ inv, const int32_t* __restrict__ rows, int64_t n, int64_t n_rows,
+                                        float* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t r = rows[i];
+  if (r >= 0 && r < n_rows) out[r] = inv[r];
+}
+
+cudaError_t launch_scatter_inv_norm(const float* inv, const int32_t* rows, int64_t n, int64_t n_rows, float* out, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  scatter_inv_norm_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(inv, rows, n, n_rows, out);
+  return cudaGetLastError();
+}
+
+// Compaction: gather the rows listed in map (and their side arrays) into bounce buffers.  One warp per row,
+// 16-byte pieces (row_bytes % 16 == 0 for bf16 dims % 8 == 0 and for f32 dims % 4 == 0; else byte loop).
+__global__ void gather_rows_kernel(const uint8_t* __restrict__ rows, const float* __restrict__ inv, const int64_t* __restrict__ ids,
+                                   const int32_t* __restrict__ user, const int32_t* __restrict__ org, const int32_t* __restrict__ map,
+                                   int64_t n, int row_bytes, uint8_t* __restrict__ o_rows, float* __restrict__ o_inv,
+                                   int64_t* __restrict__ o_ids, int32_t* __restrict__ o_user, int32_t* __restrict__ o_org) {
+  const int64_t j = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (j >= n) return;
+  const int64_t r = map[j];
+  const uint8_t* src = rows + r * row_bytes;
+  uint8_t* dst = o_rows + j * row_bytes;
+  if ((row_bytes & 15) == 0) {
+    for (int i = lane; i < row_bytes / 16; i += 32) reinterpret_cast<uint4*>(dst)[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
+  } else {
+    for (int i = lane; i < row_bytes; i += 32) dst[i] = src[i];
+  }
+  if (lane == 0) { o_inv[j] = inv[r]; o_ids[j] = ids[r]; o_user[j] = user[r]; o_org[j] = org[r]; }
+}
+
+cudaError_t launch_gather_rows(const void* rows, const float* inv, const int64_t* ids, const int32_t* user, const int32_t* org,
+                               const int32_t* map, int64_t n, int row_bytes, void* o_rows, float* o_inv, int64_t* o_ids,
+                               int32_t* o_user, int32_t* o_org, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  const int64_t blocks = (n * 32 + 255) / 256;
+  gather_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(static_cast<const uint8_t*>(rows), inv, ids, user, org, map, n,
+                                                                  row_bytes, static_cast<uint8_t*>(o_rows), o_inv, o_ids, o_user, o_org);
   return cudaGetLastError();
 }
 

@@ -363,7 +363,6 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
 #pragma unroll
             for (int j = 0; j < kTcKbPerStage; ++j) {
               if (j < nkb && !(p.dbg_flags & 2)) {
-#pragma unroll
                 const int kb = kb0 + j;
                 if (kb < kTcTmemDim / kTcKBlock) {
 #pragma unroll
@@ -522,7 +521,10 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
           published = pv0;
           atomicMax(pubrow + tset, (static_cast<unsigned long long>(p.epoch) << 32) | f32_to_ord(pv0));
         }
-        st.top1 = t1; st.top2 = t2;
+        // The main loop examines this tile again.  Only the FIFO mode may keep t1 (there top1 is an idempotent
+        // running max); the push path counts every admitted row into top1 / top2, so seeding them here would
+        // count the tile's best row twice and publish it as "second best" -- an unsound threshold when xm == 2.
+        if (L.fifo_recs > 0 && xm == 1) st.top1 = t1;
         const long long tb = clock64();
         float tboot = -INFINITY;
         do {
@@ -540,11 +542,11 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         const int b = it & 1;
         const float* nb = mynorm + (li & 1) * kTcTileN;
         const long long t_top0 = TCLK();
-        const unsigned long long thr_e = xchg ? __ldcg(thr_q) : 0ull;   // consumed after the fast path
+        const unsigned long long thr_e = (xchg && !(p.dbg_flags & 16)) ? __ldcg(thr_q) : 0ull;   // consumed after the fast path
 
         // norms of the next tile (loaded one iteration ago) -> the other buffer; start the
         // loads for the tile after that.  A whole tile period hides the HBM latency.
-        {
+        if (!(p.dbg_flags & 32)) {
           float* nnext = mynorm + ((li + 1) & 1) * kTcTileN;
           nnext[lane] = nn0; nnext[lane + 32] = nn1;
           load_norms(li + 2, nn0, nn1);
@@ -570,7 +572,7 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
           if constexpr (kCtaGroup == 2) mbar_arrive_cluster(&tmem_empty[b], 0); else mbar_arrive(&tmem_empty[b]);
         }
         t_ld += TCLK() - t_ld0;
-        if (p.dbg_flags & 1) continue;
+        if (p.dbg_flags & (1 | 4)) continue;
         const long long t_fast0 = TCLK();
 
         // Fast path: scale by 1/|c_j| in place (packed FMUL2) and keep one running max per 16
@@ -601,6 +603,7 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         }
 
         t_fast += TCLK() - t_fast0;
+        if (p.dbg_flags & 8) { st.top1 = fmaxf(st.top1, fmaxf(fmaxf(cmax[0], cmax[1]), fmaxf(cmax[2], cmax[3]))); continue; }
         const long long t_ch0 = TCLK();
         // A group of four scores whose max reaches this query's threshold goes out of line.
         if (static_cast<uint32_t>(thr_e >> 32) == p.epoch) st.tau = fmaxf(st.tau, __uint_as_float(static_cast<uint32_t>(thr_e)));

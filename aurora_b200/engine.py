@@ -130,6 +130,34 @@ class Index:
         N.check(self._lib.aur_search(self._h, _ptr(q), nq, int(k), _ptr(u), _ptr(o), _ptr(scores), _ptr(ids)))
         return ids, scores
 
+    def search_snapshot(self, queries: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray, int]:
+        """(ids, scores, snapshot_rows): the search together with the number of appended rows it saw -- with a
+        concurrent writer the answer is the top-k of exactly that prefix."""
+        q = self._rows_buffer(queries)
+        nq = q.shape[0]
+        scores = np.empty((nq, k), dtype=np.float32)
+        ids = np.empty((nq, k), dtype=np.int64)
+        snap = C.c_int64(-1)
+        N.check(self._lib.aur_search_ex(self._h, _ptr(q), nq, int(k), None, None, _ptr(scores), _ptr(ids), C.byref(snap)))
+        return ids, scores, int(snap.value)
+
+    def compact(self) -> int:
+        """Reclaim tombstoned rows (exclusive; waits for searches in flight).  Returns the rows freed."""
+        freed = C.c_int64(0)
+        N.check(self._lib.aur_compact(self._h, C.byref(freed)))
+        return int(freed.value)
+
+    def search_subset(self, queries: np.ndarray, k: int, allow_ids: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """Search restricted to the rows whose ids are listed (a resolved metadata pre-filter): the other rows'
+        inverse norms are masked on the device and the same kernels run."""
+        q = self._rows_buffer(queries)
+        nq = q.shape[0]
+        allow = np.ascontiguousarray(allow_ids, dtype=np.int64)
+        scores = np.empty((nq, k), dtype=np.float32)
+        ids = np.empty((nq, k), dtype=np.int64)
+        N.check(self._lib.aur_search_subset(self._h, _ptr(q), nq, int(k), _ptr(allow), allow.shape[0], _ptr(scores), _ptr(ids)))
+        return ids, scores
+
     def search_dev(self, q_ptr: int, nq: int, k: int, scores_ptr: int, ids_ptr: int, scores64_ptr: int = 0,
                    q_user_ptr: int = 0, q_org_ptr: int = 0, stream: int = 0) -> None:
         """Everything in HBM; asynchronous on ``stream`` (0 = the index's own stream)."""

@@ -79,9 +79,14 @@ class KnowledgeBase:
         self._lock = threading.RLock()  # the reference's module globals are unlocked (weaviate_client.py:31-32)
         self._props: Dict[int, Dict[str, Any]] = {}   # id -> properties
         self._key2id: Dict[str, int] = {}             # uuid5 -> id
+        self._id2key: Dict[int, str] = {}
+        self._by_user: Dict[str, set] = {}            # host-side inverted lists: narrow a filter's metadata scan
+        self._by_org: Dict[str, set] = {}
         self._next_id = 0
         self._user_code: Dict[str, int] = {}
         self._org_code: Dict[str, int] = {}
+        self.saved_mutations = 0
+        self.mutations = 0              # inserts + deletes since construction (the daemon's snapshot policy reads it)
 
     # ------------------------------------------------------------------ tenant codes
     def _code(self, table: Dict[str, int], key: Optional[str], create: bool) -> int:
@@ -97,7 +102,7 @@ class KnowledgeBase:
     def insert(self, user_id: str, document_id: str, source_filename: str, chunks: List[Dict[str, Any]],
                org_id: Optional[str] = None) -> int:
         now = datetime.now(timezone.utc).isoformat()          # weaviate_client.py:165
-        texts, metas = [], []
+        objs = []
         for chunk in chunks:
             try:
                 chunk_index = chunk.get("chunk_index", 0)
@@ -110,77 +115,126 @@ class KnowledgeBase:
                     props["org_id"] = org_id               # weaviate_client.py:183-184
                 key = generate_uuid5(f"{user_id}:{document_id}:{chunk_index}")
                 heading = props["heading_context"]
-                texts.append((heading + "\n" if heading else "") + props["content"])
-                metas.append((key, props))
+                objs.append((key, props, (heading + "\n" if heading else "") + props["content"]))
             except Exception as e:  # per-object failure: counted out, not fatal (weaviate_client.py:189-190)
                 logger.error(f"[KB B200] Error adding chunk: {e}")
-        if not metas:
+        return self.insert_objects(objs, user_id, org_id)
+
+    def insert_objects(self, objs: List[Tuple[str, Dict[str, Any], str]], user_id: Optional[str],
+                       org_id: Optional[str] = None) -> int:
+        """Upsert ``(uuid key, properties, text to embed)`` objects of one tenant: the text is encoded on the
+        GPU and the vector appended to the shard; an existing key replaces its old vector and properties."""
+        if not objs:
             return 0
+        texts = [t for _, _, t in objs]
         fused = hasattr(self.encoder, "encode_append") and hasattr(self.index, "_h")   # CUDA encoder + CUDA shard
         vecs = None if fused else self.encoder.encode(texts)
         with self._lock:
-            ids = np.empty(len(metas), dtype=np.int64)
-            for i, (key, _) in enumerate(metas):
+            ids = np.empty(len(objs), dtype=np.int64)
+            for i, (key, _, _) in enumerate(objs):
                 if key not in self._key2id:
                     self._key2id[key] = self._next_id
+                    self._id2key[self._next_id] = key
                     self._next_id += 1
                 ids[i] = self._key2id[key]
-            ucode = np.full(len(metas), self._code(self._user_code, user_id, True), dtype=np.int32)
-            ocode = np.full(len(metas), self._code(self._org_code, org_id, True), dtype=np.int32)
+            ucode = np.full(len(objs), self._code(self._user_code, user_id, True), dtype=np.int32)
+            ocode = np.full(len(objs), self._code(self._org_code, org_id, True), dtype=np.int32)
             if fused:
                 self.encoder.encode_append(self.index, texts, ids, ucode, ocode)
             else:
                 self.index.add(vecs, ids, ucode, ocode)
-            for i, (_, props) in enumerate(metas):
-                self._props[int(ids[i])] = props
-                self.sparse.add(int(ids[i]), texts[i])
-        return len(metas)
+            for i, (_, props, text) in enumerate(objs):
+                rid = int(ids[i])
+                old = self._props.get(rid)
+                if old is not None:
+                    self._unindex(rid, old)
+                self._props[rid] = props
+                self._by_user.setdefault(props.get("user_id"), set()).add(rid)
+                if props.get("org_id"):
+                    self._by_org.setdefault(props["org_id"], set()).add(rid)
+                self.sparse.add(rid, text)
+            self.mutations += len(objs)
+        return len(objs)
+
+    def _unindex(self, rid: int, props: Dict[str, Any]) -> None:
+        self._by_user.get(props.get("user_id"), set()).discard(rid)
+        if props.get("org_id"):
+            self._by_org.get(props["org_id"], set()).discard(rid)
 
     # ------------------------------------------------------------------ search
     def query(self, query: str, limit: int, filters=None, user_id: Optional[str] = None,
-              org_id: Optional[str] = None, alpha: Optional[float] = None) -> List[SimpleNamespace]:
+              org_id: Optional[str] = None, alpha: Optional[float] = None, scoped: bool = False) -> List[SimpleNamespace]:
         """Top-``limit`` objects.  ``alpha`` None or >= 1: pure vector search, ``score`` = cosine
         (near_text, incident_feedback/weaviate_client.py:286-297).  ``alpha`` < 1: hybrid with ranked
         fusion (weaviate_client.py:252-259): dense and BM25 lists fused as alpha/(rank+60) +
-        (1-alpha)/(rank+60), ``score`` = the fused score.  Tenant scope (user OR org) runs inside the
-        kernel for the dense leg and as a pre-filter for the keyword leg; any extra ``filters``
-        expression is applied to the metadata of the over-fetched lists."""
+        (1-alpha)/(rank+60), ``score`` = the fused score.
+
+        Filters are PRE-filters, as in Weaviate: the tenant scope (user OR org) runs inside the kernel;
+        a ``filters`` expression is resolved against the metadata table to the set of allowed ids, and
+        the kernel then searches only those rows (``Index.search_subset``), so a small tenant's chunks
+        are found even when the global top-k belongs to other tenants.
+
+        ``scoped``: the caller is a tenant-facing entry point (search_knowledge_base): a missing user AND
+        org matches nothing instead of everything (the reference always applies ``user_id == u``,
+        weaviate_client.py:244-249)."""
         if limit <= 0:
+            return []
+        if scoped and not user_id and not org_id:
             return []
         hybrid = alpha is not None and alpha < 1.0
         dense_w = 1.0 if not hybrid else max(0.0, float(alpha))
         qv = self.encoder.encode([query]) if dense_w > 0.0 else None
         with self._lock:
-            def ok(props) -> bool:
-                return props is not None and (filters is None or filters.matches(props))
+            tenant = scoped or user_id is not None or org_id is not None
+
+            def tenant_ok(props) -> bool:
+                if not tenant:
+                    return True
+                return (bool(user_id) and props.get("user_id") == user_id) or \
+                       (bool(org_id) and props.get("org_id") == org_id)
+
+            allowed: Optional[List[int]] = None
+            if filters is not None:
+                # narrow the scan with the filter's own equality terms and the tenant scope, then run the predicate
+                eq = filters.required_equalities()
+                pools = []
+                if "org_id" in eq:
+                    pools.append(self._by_org.get(eq["org_id"], set()))
+                if "user_id" in eq:
+                    pools.append(self._by_user.get(eq["user_id"], set()))
+                if tenant:
+                    pools.append(self._by_user.get(user_id, set()) | (self._by_org.get(org_id, set()) if org_id else set()))
+                cand = set.intersection(*pools) if pools else self._props.keys()
+                allowed = [rid for rid in cand if filters.matches(self._props[rid]) and tenant_ok(self._props[rid])]
 
             dense: List[Tuple[int, float]] = []
-            if qv is not None:
-                q_user = q_org = None
-                if user_id is not None or org_id is not None:
-                    q_user = np.array([self._code(self._user_code, user_id, False) if user_id else -2], dtype=np.int32)
-                    q_org = np.array([self._code(self._org_code, org_id, False) if org_id else -1], dtype=np.int32)
-                    if q_org[0] == -2:
-                        q_org[0] = -1
-                fetch = limit if (filters is None and not hybrid) else _MAX_FETCH
-                fetch = max(1, min(_MAX_FETCH, fetch))
-                ids, scores = self.index.search(qv, fetch, q_user, q_org)
+            if qv is not None and (allowed is None or allowed):
+                fetch = max(1, min(_MAX_FETCH, limit if not hybrid else _MAX_FETCH))
+                if allowed is not None:
+                    ids, scores = self.index.search_subset(qv, fetch, np.asarray(allowed, dtype=np.int64))
+                else:
+                    q_user = q_org = None
+                    if tenant:
+                        q_user = np.array([self._code(self._user_code, user_id, False) if user_id else -2], dtype=np.int32)
+                        q_org = np.array([self._code(self._org_code, org_id, False) if org_id else -1], dtype=np.int32)
+                        if q_org[0] == -2:
+                            q_org[0] = -1
+                    ids, scores = self.index.search(qv, fetch, q_user, q_org)
                 for rid, sc in zip(ids[0], scores[0]):
                     if rid < 0:
                         break
-                    if ok(self._props.get(int(rid))):
+                    if int(rid) in self._props:
                         dense.append((int(rid), float(sc)))
             if not hybrid:
                 picked = [(rid, sc, sc) for rid, sc in dense[:limit]]
             else:
+                allowed_set = None if allowed is None else set(allowed)
+
                 def allow(doc: int) -> bool:
+                    if allowed_set is not None:
+                        return doc in allowed_set
                     props = self._props.get(doc)
-                    if not ok(props):
-                        return False
-                    if user_id is None and org_id is None:
-                        return True
-                    return (user_id is not None and props.get("user_id") == user_id) or \
-                           (bool(org_id) and props.get("org_id") == org_id)
+                    return props is not None and tenant_ok(props)
 
                 sparse = self.sparse.search(query, _MAX_FETCH, allow)
                 from .bm25 import ranked_fusion
@@ -191,7 +245,7 @@ class KnowledgeBase:
             out = []
             for rid, score, cosine in picked:
                 meta = SimpleNamespace(score=float(score), distance=None if cosine is None else 1.0 - float(cosine))
-                out.append(SimpleNamespace(properties=dict(self._props[rid]), uuid=None, metadata=meta))
+                out.append(SimpleNamespace(properties=dict(self._props[rid]), uuid=self._id2key.get(rid), metadata=meta))
             return out
 
     # ------------------------------------------------------------------ persistence
@@ -202,21 +256,38 @@ class KnowledgeBase:
 
         os.makedirs(directory, exist_ok=True)
         with self._lock:
-            self.index.save(os.path.join(directory, "shard"))
-            meta = {"version": 1, "dim": self.dim, "next_id": self._next_id, "user_code": self._user_code,
+            # both files are written beside their final names and renamed, shard first: a crash leaves either the
+            # old pair or the new pair (meta.json names the shard generation it belongs to)
+            gen = int(self.mutations)
+            tmp_shard = os.path.join(directory, "shard.tmp")
+            self.index.save(tmp_shard)
+            os.replace(tmp_shard + ".npz", os.path.join(directory, f"shard.{gen}.npz"))
+            meta = {"shard": f"shard.{gen}.npz","version": 1, "dim": self.dim, "next_id": self._next_id, "user_code": self._user_code,
                     "org_code": self._org_code, "key2id": self._key2id,
                     "props": {str(k): v for k, v in self._props.items()}}
             tmp = os.path.join(directory, "meta.json.tmp")
             with open(tmp, "w", encoding="utf-8") as f:
                 json.dump(meta, f)
             os.replace(tmp, os.path.join(directory, "meta.json"))
+            for name in os.listdir(directory):     # older generations are garbage once meta.json points at the new one
+                if name.startswith("shard.") and name.endswith(".npz") and name != meta["shard"]:
+                    try:
+                        os.remove(os.path.join(directory, name))
+                    except OSError:
+                        pass
+            self.saved_mutations = gen
 
     @classmethod
-    def load(cls, directory: str, encoder, capacity: int = 1 << 20, device: int = 0, index_loader=None) -> "KnowledgeBase":
+    def load(cls, directory: str, encoder, capacity: int = 1 << 20, device: int = 0, index_loader=None,
+             text_of: Optional[Callable[[Dict[str, Any]], str]] = None) -> "KnowledgeBase":
         """Rebuild from ``save``: vectors go back into HBM as they were stored (no re-encoding), the
         keyword index is rebuilt from the chunk texts."""
         import json
 
+        if text_of is None:
+            def text_of(p):
+                heading = p.get("heading_context", "")
+                return (heading + "\n" if heading else "") + p.get("content", "")
         with open(os.path.join(directory, "meta.json"), encoding="utf-8") as f:
             meta = json.load(f)
         if int(meta["dim"]) != int(encoder.dim):
@@ -226,16 +297,19 @@ class KnowledgeBase:
 
             def index_loader(path, cap):
                 return Index.load(path, capacity=cap, device=device)
-        loaded = index_loader(os.path.join(directory, "shard"), int(capacity))
+        loaded = index_loader(os.path.join(directory, meta.get("shard", "shard.npz")), int(capacity))
         kb = cls(encoder, capacity=capacity, device=device, index_factory=lambda dim, cap: loaded)
         kb._next_id = int(meta["next_id"])
         kb._user_code = {k: int(v) for k, v in meta["user_code"].items()}
         kb._org_code = {k: int(v) for k, v in meta["org_code"].items()}
         kb._key2id = {k: int(v) for k, v in meta["key2id"].items()}
+        kb._id2key = {v: k for k, v in kb._key2id.items()}
         kb._props = {int(k): v for k, v in meta["props"].items()}
         for rid, p in kb._props.items():
-            heading = p.get("heading_context", "")
-            kb.sparse.add(rid, (heading + "\n" if heading else "") + p.get("content", ""))
+            kb._by_user.setdefault(p.get("user_id"), set()).add(rid)
+            if p.get("org_id"):
+                kb._by_org.setdefault(p["org_id"], set()).add(rid)
+            kb.sparse.add(rid, text_of(p))
         return kb
 
     # ------------------------------------------------------------------ deletes / counts
@@ -249,8 +323,10 @@ class KnowledgeBase:
                 self.index.remove(np.array(ids, dtype=np.int64))
                 for rid in ids:
                     p = self._props.pop(rid)
+                    self._unindex(rid, p)
                     self.sparse.remove(rid)
-                    self._key2id.pop(generate_uuid5(f"{p['user_id']}:{p['document_id']}:{p['chunk_index']}"), None)
+                    self._key2id.pop(self._id2key.pop(rid, None), None)
+                self.mutations += len(ids)
             return len(ids)
 
     def count_where(self, pred) -> int:
@@ -349,7 +425,7 @@ def search_knowledge_base(user_id: str, query: str, limit: int = 5, alpha: float
     if not query.strip():
         return []
     try:
-        objs = _get_kb().query(query, limit, user_id=user_id, org_id=org_id, alpha=alpha)
+        objs = _get_kb().query(query, limit, user_id=user_id, org_id=org_id, alpha=alpha, scoped=True)
         results = []
         for obj in objs:
             score = obj.metadata.score if obj.metadata else 0.0

@@ -25,8 +25,11 @@
  *     server/routes/incident_feedback/weaviate_client.py:296-297), NOT clamped;
  *     results are ordered (score desc, id asc); missing results are padded with
  *     id -1 / score -INFINITY;
- *   - all entry points are thread-safe (one internal mutex per index) and never touch
- *     the Python GIL.
+ *   - all entry points are thread-safe and never touch the Python GIL.  The shard is append-only
+ *     with a published row count: a search scans exactly the rows that were published when it was
+ *     enqueued (a consistent prefix) and never waits for a writer; several searches may be in
+ *     flight at once, each with its own scratch (see aur_search_ex); writers are serialised among
+ *     themselves; aur_compact / aur_export are exclusive.
  */
 #ifndef AURORA_B200_H_
 #define AURORA_B200_H_
@@ -109,6 +112,12 @@ int aur_add_dev(aur_index* ix, const void* rows_dev, const int64_t* ids_host,
 int aur_export(aur_index* ix, void* rows_out, int64_t* ids_out, int32_t* user_out,
                int32_t* org_out, uint8_t* live_out, int64_t n);
 
+/* Reclaims the tombstones left by upserts and deletes (the reference's prediscovery job deletes and
+ * re-inserts its chunks periodically, weaviate_client.py:374-394): live rows move down in append order,
+ * aur_stats.rows drops to aur_stats.live.  Exclusive: waits for in-flight searches.  *reclaimed
+ * (nullable) receives the number of rows freed. */
+int aur_compact(aur_index* ix, int64_t* reclaimed);
+
 /* Deletes.  Replaces collection.data.delete_many(where=...) (weaviate_client.py:309,
  * :336, :387): the Python layer resolves the filter to ids; rows become tombstones.
  * *removed receives how many ids were live. */
@@ -124,6 +133,21 @@ int aur_remove(aur_index* ix, const int64_t* ids, int64_t n, int64_t* removed);
 int aur_search(aur_index* ix, const void* queries_host, int32_t nq, int32_t k,
                const int32_t* q_user, const int32_t* q_org,
                float* scores_out, int64_t* ids_out);
+/* Same call, additionally reporting the snapshot it answered from: *snapshot_rows_out = number of
+ * appended rows (tombstones included) that were visible to this search.  With a writer appending
+ * concurrently (the reference: Celery ingest workers next to gunicorn search threads,
+ * docker-compose.yaml:191,283-285) the answer is the top-k of exactly that prefix. */
+int aur_search_ex(aur_index* ix, const void* queries_host, int32_t nq, int32_t k,
+                  const int32_t* q_user, const int32_t* q_org,
+                  float* scores_out, int64_t* ids_out, int64_t* snapshot_rows_out);
+/* Search restricted to the rows whose ids are listed: a metadata pre-filter the Python layer has
+ * resolved to ids, e.g. `org_id == o AND document_id LIKE "discovery:*"`
+ * (server/chat/background/rca_prompt_builder.py:286-298) or Aurora Learn's org scope
+ * (server/routes/incident_feedback/weaviate_client.py:279-291).  Weaviate pre-filters the same way
+ * (allow-list, then vector search).  Unknown ids are ignored; n_allow = 0 returns only padding. */
+int aur_search_subset(aur_index* ix, const void* queries_host, int32_t nq, int32_t k,
+                      const int64_t* allow_ids, int64_t n_allow,
+                      float* scores_out, int64_t* ids_out);
 /* Device variant: everything in HBM; scores64_dev (nullable) additionally receives the
  * fp64 ranking keys needed for an exact cross-shard merge. */
 int aur_search_dev(aur_index* ix, const void* queries_dev, int32_t nq, int32_t k,
@@ -145,6 +169,26 @@ int aur_merge_topk_dev(int32_t device, const double* in_scores64, const int64_t*
 int aur_merge_topk_packed_dev(int32_t device, const void* packed, int32_t n_shards, int32_t nq,
                               int32_t k, float* out_scores, int64_t* out_ids,
                               double* out_scores64, void* stream);
+
+/* Fused exchange ("fused variant"): instead of a local top-k array + ncclAllGather + merge, the
+ * kernel that produces a shard's exact top-k stores it straight into EVERY rank's exchange buffer over NVLink
+ * (peer-mapped through CUDA IPC), and the merge kernel that follows waits on per-rank delivery flags.  One
+ * process per GPU:
+ *   1. every rank:  aur_exchange_create(...)      -> its 64-byte IPC handle
+ *   2. all-gather the handles (any host transport: torch.distributed, MPI, a file)
+ *   3. every rank:  aur_exchange_connect(ex, all_handles)
+ *   4. per batch, every rank, in lock step: aur_search_exchange_dev(ix, ex, queries, ...) -- on return of the
+ *      stream's work scores_dev / ids_dev hold the GLOBAL top-k on every rank (ids must be globally unique).
+ * All ranks must call step 4 the same number of times; barrier before aur_exchange_close. */
+typedef struct aur_exchange aur_exchange;
+int aur_exchange_create(int32_t device, int32_t rank, int32_t world, int32_t nq_max, int32_t k_max,
+                        aur_exchange** out, uint8_t* handle_out /* [64] */);
+int aur_exchange_connect(aur_exchange* ex, const uint8_t* all_handles /* [world][64] */);
+int aur_exchange_close(aur_exchange* ex);
+/* exchanges completed on this rank; *status != 0: a peer did not deliver within the kernel's time-out */
+int aur_exchange_status(aur_exchange* ex, int64_t* exchanges_done, int32_t* status);
+int aur_search_exchange_dev(aur_index* ix, aur_exchange* ex, const void* queries_dev, int32_t nq,
+                            int32_t k, float* scores_dev, int64_t* ids_dev, void* stream);
 
 /* Pairwise cosine of row i of a with row i of b (host buffers, fp32 in, fp64 out).
  * Replaces SimilarityStrategy._cosine_similarity

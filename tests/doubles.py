@@ -63,6 +63,11 @@ class OracleIndex:
         return O.cosine_topk(q, self.rows, k, ids=self.ids, live=self.live, row_user=self.user, row_org=self.org,
                              q_user=q_user, q_org=q_org)
 
+    def search_subset(self, queries, k, allow_ids):
+        q = O.round_to_bf16(np.asarray(queries, dtype=np.float32))
+        live = self.live & np.isin(self.ids, np.asarray(allow_ids, dtype=np.int64))
+        return O.cosine_topk(q, self.rows, k, ids=self.ids, live=live)
+
     def save(self, path):
         np.savez(path, rows=self.rows[self.live], ids=self.ids[self.live], user=self.user[self.live], org=self.org[self.live],
                  dim=self.dim, capacity=self.capacity)

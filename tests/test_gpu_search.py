@@ -138,6 +138,31 @@ def test_tcgen05_parity(kernel, n, d, nq, k):
     _check(ids, sc, *O.cosine_topk(Q, C, k))
 
 
+@pytest.mark.parametrize("kernel", [N.KERNEL_TC1, N.KERNEL_TC2])
+@pytest.mark.parametrize("tiles_per_pair", [1, 2, 5])
+def test_one_strong_row_per_tile_large_k(kernel, tiles_per_pair):
+    """Adversarial for the threshold exchange with two published values per CTA (k + slack > 74 CTA pairs,
+    i.e. k >= 67): every 64-row tile holds exactly one row close to the query and 63 unrelated ones, so a
+    CTA that counted its best row twice would certify a threshold only ~half of the claimed rows reach and
+    the tail of the top-128 would be dropped.  Also the shape a tenant mask produces (about one visible
+    row per tile)."""
+    d, nq, k = 768, 6, 128
+    n = 74 * 64 * tiles_per_pair
+    rng = np.random.default_rng(tiles_per_pair)
+    C = rng.standard_normal((n, d)).astype(np.float32)
+    Q = rng.standard_normal((nq, d)).astype(np.float32)
+    for t in range(n // 64):
+        for i in range(nq):
+            C[t * 64 + (7 * i + t) % 64] = Q[i] * (1.0 + 0.01 * i) + 0.05 * rng.standard_normal(d).astype(np.float32)
+    C, Q = O.round_to_bf16(C), O.round_to_bf16(Q)
+    with Index(d, n) as ix:
+        ix.add(C, np.arange(n, dtype=np.int64))
+        ix.set_kernel(kernel)
+        ids, sc = ix.search(Q, k)
+    assert (ids >= 0).all()
+    _check(ids, sc, *O.cosine_topk(Q, C, k))
+
+
 def test_large_k_at_dim_1024_falls_back_in_auto_mode():
     """dim 1024 with k = 128: the lists (k + slack per query) plus the shared-memory part of
     the queries leave no room for a TMA ring, so AUTO serves it with the generic kernel and an explicit
@@ -379,10 +404,10 @@ def test_sharded_searcher_single_rank_on_gpu():
 
 
 def test_concurrent_ingest_and_search_threads():
-    """BASELINE config 5's access pattern in miniature: one thread appends chunk batches while others search
-    (the reference is hit from gunicorn threads and Celery workers at once; every entry point takes the
-    shard's mutex).  Every answer must be a valid top-k of SOME prefix of the appended rows: ids below the
-    row count seen after the call, scores non-increasing, and the planted exact match on top once present."""
+    """BASELINE config 5's access pattern in miniature: one thread appends chunk batches while three others search
+    (the reference is hit from gunicorn threads and Celery workers at once).  The shard publishes its row count
+    only after a batch has landed and a search scans exactly the prefix published when it was enqueued, so EVERY
+    answer must equal the oracle's top-k of exactly the prefix the call reports (aur_search_ex) -- ids bit-exact."""
     import threading
 
     d, k, batches, per = 768, 8, 24, 512
@@ -390,7 +415,8 @@ def test_concurrent_ingest_and_search_threads():
     Q = O.round_to_bf16(rng.standard_normal((32, d)).astype(np.float32))
     blocks = [O.round_to_bf16(rng.standard_normal((per, d)).astype(np.float32)) for _ in range(batches)]
     blocks[5][7] = Q[3]                                    # exact match appears with batch 5 (id 5*512+7)
-    errors, done = [], threading.Event()
+    C = np.concatenate(blocks)
+    errors, done, answers = [], threading.Event(), []
     with Index(d, batches * per) as ix:
         def writer():
             try:
@@ -401,24 +427,99 @@ def test_concurrent_ingest_and_search_threads():
             finally:
                 done.set()
 
-        def reader():
+        def reader(slot):
             try:
-                while not done.is_set():
-                    ids, sc = ix.search(Q, k)
-                    rows_after = ix.stats()["rows"]
-                    valid = ids >= 0
-                    assert np.all(ids[valid] < rows_after)
-                    both = valid[:, 1:] & valid[:, :-1]                     # (fewer than k rows early on: padded tail)
-                    assert np.all((sc[:, 1:] <= sc[:, :-1] + 1e-6) | ~both)
-                    assert not np.any(valid[:, 1:] & ~valid[:, :-1])         # padding only at the end
-                    if rows_after >= 6 * per and valid[3, 0] and (ids[3] == 5 * per + 7).any():
-                        assert ids[3, 0] == 5 * per + 7 and sc[3, 0] > 0.9999
+                mine = []
+                while not done.is_set() or len(mine) < 2:
+                    ids, sc, snap = ix.search_snapshot(Q, k)
+                    assert snap % per == 0 and 0 <= snap <= batches * per       # only whole, landed batches are visible
+                    mine.append((snap, ids, sc))
+                answers.append(mine)
             except Exception as e:      # pragma: no cover
                 errors.append(e)
 
-        ts = [threading.Thread(target=writer)] + [threading.Thread(target=reader) for _ in range(3)]
+        ts = [threading.Thread(target=writer)] + [threading.Thread(target=reader, args=(i,)) for i in range(3)]
         [t.start() for t in ts]; [t.join() for t in ts]
         assert not errors, errors[0]
         ids, sc = ix.search(Q, k)
-        C = np.concatenate(blocks)
     _check(ids, sc, *O.cosine_topk(Q, C, k))
+    seen = set()
+    oracle = {}
+    for mine in answers:
+        snaps = [s_ for s_, _, _ in mine]
+        assert snaps == sorted(snaps)                                         # a thread never sees the shard shrink
+        for snap, ids_t, sc_t in mine:
+            seen.add(snap)
+            if snap not in oracle:
+                if snap == 0:
+                    oracle[0] = (np.full((32, k), -1, np.int64), np.full((32, k), -np.inf, np.float32))
+                else:
+                    oracle[snap] = O.cosine_topk(Q, C[:snap], k)
+            _check(ids_t, sc_t, *oracle[snap])
+    assert len(seen) >= 2                                                      # readers really overlapped the writer
+
+
+def test_search_subset_is_a_pre_filter():
+    """aur_search_subset: a resolved metadata filter (ids) restricts the scan itself -- the allowed rows are found even
+    when thousands of better-scoring rows exist outside the list.  tcgen05 and generic kernels, with tombstones."""
+    n, d, nq, k = 40000, 768, 5, 10
+    C, Q = _data(n, d, nq, seed=21)
+    rng = np.random.default_rng(3)
+    ext = np.arange(n, dtype=np.int64) * 2 + 1
+    allow_rows = np.sort(rng.choice(n, size=300, replace=False))
+    live = np.zeros(n, dtype=bool); live[allow_rows] = True
+    with Index(d, n) as ix:
+        ix.add(C, ext)
+        dead = allow_rows[:7]
+        ix.remove(ext[dead]); live[dead] = False
+        unknown = np.array([10**12, 4], dtype=np.int64)                          # ids that do not exist are ignored
+        for kern in (N.KERNEL_AUTO, N.KERNEL_SIMT):
+            ix.set_kernel(kern)
+            ids, sc = ix.search_subset(Q, k, np.concatenate([ext[allow_rows], unknown]))
+            _check(ids, sc, *O.cosine_topk(Q, C, k, ids=ext, live=live))
+        ix.set_kernel(N.KERNEL_AUTO)
+        assert ix.stats()["last_kernel"] in (N.KERNEL_SIMT, N.KERNEL_TC2)
+        few, _ = ix.search_subset(Q, k, ext[allow_rows[7:10]])
+        assert (few[:, :3] >= 0).all() and (few[:, 3:] == -1).all()
+        none, _ = ix.search_subset(Q, k, np.zeros(0, dtype=np.int64))
+        assert (none == -1).all()
+        ids_all, sc_all = ix.search(Q, k)                                        # the mask does not leak into plain searches
+        live_all = np.ones(n, dtype=bool); live_all[dead] = False
+        _check(ids_all, sc_all, *O.cosine_topk(Q, C, k, ids=ext, live=live_all))
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f32"])
+def test_compaction_reclaims_tombstones(dtype):
+    """Upserts and deletes leave dead rows behind (the prediscovery job re-inserts its chunks periodically,
+    weaviate_client.py:374-394); aur_compact moves the live rows down so the shard never fills up with them."""
+    n, d, nq, k = 9000, 256, 9, 12
+    C, Q = _data(n, d, nq, seed=8, bf16=(dtype == "bf16"))
+    rng = np.random.default_rng(4)
+    with Index(d, n, dtype=dtype) as ix:
+        ix.add(C, np.arange(n, dtype=np.int64))
+        dead = rng.choice(n, size=3000, replace=False)
+        assert ix.remove(dead) == 3000
+        with pytest.raises(N.AuroraError):                                        # full: 9000 + 1 > capacity
+            ix.add(C[:1], np.array([n + 5], dtype=np.int64))
+        live = np.ones(n, dtype=bool); live[dead] = False
+        before = ix.search(Q, k)
+        assert ix.compact() == 3000
+        st = ix.stats()
+        assert st["rows"] == n - 3000 and st["live"] == n - 3000
+        after = ix.search(Q, k)
+        assert np.array_equal(before[0], after[0]) and np.array_equal(before[1], after[1])
+        _check(*after, *O.cosine_topk(Q, C, k, live=live))
+        assert ix.compact() == 0
+        # the freed space is usable again, ids keep resolving (upsert of a moved row, delete of another)
+        ix.add(C[dead[:100]], dead[:100].astype(np.int64))
+        live[dead[:100]] = True
+        survivor = int(np.nonzero(live)[0][-1])
+        ix.add(Q[:1], np.array([survivor], dtype=np.int64))                       # replaces that id's vector with query 0
+        C2 = C.copy(); C2[survivor] = Q[0]
+        ids2, sc2 = ix.search(Q, k)
+        assert ids2[0, 0] == survivor
+        rows, ids_e, _, _, live_e = ix.export()
+        order = {int(i): r for r, i in enumerate(ids_e) if live_e[r]}
+        assert len(order) == int(live.sum())
+    ref_ids, ref_sc = O.cosine_topk(Q, C2, k, live=live)
+    _check(ids2, sc2, ref_ids, ref_sc)

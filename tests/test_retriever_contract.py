@@ -201,3 +201,43 @@ def test_filter_algebra():
     assert Filter.by_property("created_at").less_than("2027").matches(p)
     assert (Filter.by_property("org_id").equal("x") | Filter.by_property("org_id").equal("o")).matches(p)
     assert not (Filter.by_property("org_id").equal("x") & Filter.by_property("org_id").equal("o")).matches(p)
+
+
+def test_missing_tenant_matches_nothing(kb):
+    """The reference always applies ``user_id == u`` (weaviate_client.py:244-249): a missing user and org must
+    return [] -- never every tenant's chunks."""
+    kb.insert_chunks("alice", "d1", "a.md", _chunks("alpha incident postmortem"), org_id="acme")
+    assert kb.search_knowledge_base(None, "alpha incident") == []
+    assert kb.search_knowledge_base("", "alpha incident", alpha=1.0) == []
+    assert kb.search_knowledge_base("", "alpha incident", alpha=0.0) == []          # keyword leg too
+    shared = kb.search_knowledge_base(None, "alpha incident", org_id="acme")          # org scope alone still works
+    assert {r["document_id"] for r in shared} == {"d1"}
+
+
+def test_filters_are_pre_filters_not_post_filters(kb):
+    """Weaviate applies `filters` before the vector search.  With > 128 better-matching chunks owned by other
+    tenants, a post-filter over the global top-128 would return nothing for the small org."""
+    for i in range(20):
+        kb.insert_chunks(f"user{i}", f"doc{i}", "big.md",
+                         _chunks(*[f"checkout depends on payments and redis replica {j}" for j in range(10)]), org_id="big")
+    kb.insert_chunks("u", "discovery:20260101:ab", "gke-topology", _chunks("checkout depends on payments"), org_id="small")
+    _, collection = kb._get_weaviate_client()
+    f = Filter.by_property("org_id").equal("small") & Filter.by_property("document_id").like("discovery:*")
+    for alpha in (1.0, 0.5):
+        resp = collection.query.hybrid(query="checkout depends on payments and redis replica", limit=3, alpha=alpha,
+                                       fusion_type=HybridFusion.RANKED, filters=f, return_metadata=["score"])
+        assert [o.properties["source_filename"] for o in resp.objects] == ["gke-topology"]
+    near = collection.query.near_text(query="checkout payments", limit=5, filters=Filter.by_property("org_id").equal("nobody"))
+    assert near.objects == []
+
+
+def test_filter_wire_format_roundtrip():
+    f = (Filter.by_property("org_id").equal("o") & Filter.by_property("document_id").like("discovery:*")) | \
+        Filter.by_property("created_at").less_than("2027")
+    g = Filter.from_json(__import__("json").loads(__import__("json").dumps(f.to_json())))
+    for p in ({"org_id": "o", "document_id": "discovery:1"}, {"org_id": "x", "created_at": "2026"}, {"org_id": "x"}):
+        assert f.matches(p) == g.matches(p)
+    assert (Filter.by_property("org_id").equal("o") & Filter.by_property("document_id").like("d*")).required_equalities() == {"org_id": "o"}
+    assert f.required_equalities() == {}            # an OR at the root guarantees nothing
+    with pytest.raises(ValueError):
+        Filter.from_json(["exec", "x", 1])
