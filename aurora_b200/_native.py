@@ -12,6 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AURORA_B200_LIB") or os.path.join(HERE, "libaurora_b200.so")   # override: A/B kernel builds
 
+ABI_VERSION = 2          # must equal AUR_ABI_VERSION of the library that gets loaded (struct layouts below)
 AUR_OK = 0
 AUR_ERR_INVALID, AUR_ERR_CUDA, AUR_ERR_NOMEM, AUR_ERR_UNSUPPORTED, AUR_ERR_NO_DEVICE = -1, -2, -3, -4, -5
 AUR_BF16, AUR_F32 = 0, 1
@@ -21,12 +22,13 @@ KERNEL_NAMES = {0: "auto", 1: "simt", 2: "tcgen05-cta1", 3: "tcgen05-cta2"}
 # every symbol include/aurora_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "aur_abi_version", "aur_last_error", "aur_device_count", "aur_open", "aur_close", "aur_get_stats",
-    "aur_set_option", "aur_sync", "aur_add", "aur_add_dev", "aur_export", "aur_compact", "aur_remove", "aur_search", "aur_search_ex", "aur_search_subset", "aur_search_dev",
+    "aur_set_option", "aur_sync", "aur_add", "aur_add_dev", "aur_export", "aur_read_rows", "aur_compact", "aur_remove", "aur_search", "aur_search_ex", "aur_search_subset", "aur_search_dev",
     "aur_merge_topk_dev", "aur_merge_topk_packed_dev", "aur_exchange_create", "aur_exchange_connect", "aur_exchange_close",
     "aur_exchange_status", "aur_search_exchange_dev", "aur_cosine_pairs", "aur_dev_malloc", "aur_dev_free", "aur_memcpy_h2d", "aur_memcpy_d2h",
     "aur_debug_tc_scores",
     "aur_encoder_open", "aur_encoder_close", "aur_encoder_load", "aur_encode", "aur_encode_append",
-    "aur_encoder_get_stats", "aur_debug_gemm", "aur_debug_attention", "aur_debug_encoder_hidden",
+    "aur_encoder_get_stats", "aur_tokenizer_open", "aur_tokenizer_open_mem", "aur_tokenizer_close", "aur_tokenizer_info",
+    "aur_tokenize", "aur_encode_text_append", "aur_debug_gemm", "aur_debug_attention", "aur_debug_encoder_hidden",
 ]
 
 
@@ -38,7 +40,8 @@ class AurConfig(C.Structure):
 class AurStats(C.Structure):
     _fields_ = [("rows", C.c_int64), ("live", C.c_int64), ("capacity", C.c_int64), ("dim", C.c_int32),
                 ("dtype", C.c_int32), ("last_kernel", C.c_int32), ("last_launches", C.c_int32),
-                ("last_kernel_ms", C.c_float), ("last_total_ms", C.c_float)]
+                ("last_kernel_ms", C.c_float), ("last_total_ms", C.c_float), ("last_finalize_ms", C.c_float),
+                ("last_merge_ms", C.c_float)]
 
 
 class AurEncoderConfig(C.Structure):
@@ -91,6 +94,7 @@ def load():
         "aur_export": (C.c_int, [vp, vp, vp, vp, vp, vp, i64]),
         "aur_remove": (C.c_int, [vp, vp, i64, C.POINTER(i64)]),
         "aur_compact": (C.c_int, [vp, C.POINTER(i64)]),
+        "aur_read_rows": (C.c_int, [vp, i64, i64, vp, vp]),
         "aur_search_ex": (C.c_int, [vp, vp, i32, i32, vp, vp, vp, vp, C.POINTER(i64)]),
         "aur_search_subset": (C.c_int, [vp, vp, i32, i32, vp, i64, vp, vp]),
         "aur_search": (C.c_int, [vp, vp, i32, i32, vp, vp, vp, vp]),
@@ -114,13 +118,24 @@ def load():
         "aur_encode": (C.c_int, [vp, vp, vp, i32, vp, vp]),
         "aur_encode_append": (C.c_int, [vp, vp, vp, vp, i32, vp, vp, vp]),
         "aur_encoder_get_stats": (C.c_int, [vp, C.POINTER(AurEncoderStats)]),
+        "aur_tokenizer_open": (C.c_int, [C.c_char_p, i32, C.POINTER(vp)]),
+        "aur_tokenizer_open_mem": (C.c_int, [C.c_char_p, i64, i32, C.POINTER(vp)]),
+        "aur_tokenizer_close": (C.c_int, [vp]),
+        "aur_tokenizer_info": (C.c_int, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+        "aur_tokenize": (C.c_int, [vp, C.c_char_p, vp, i32, i32, vp, i64, vp, i32]),
+        "aur_encode_text_append": (C.c_int, [vp, vp, vp, C.c_char_p, vp, i32, i32, i32, i32, vp, vp, vp, i32]),
         "aur_debug_gemm": (C.c_int, [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, C.POINTER(C.c_float)]),
         "aur_debug_attention": (C.c_int, [i32, vp, vp, i32, i32, i32, vp, C.POINTER(C.c_float)]),
         "aur_debug_encoder_hidden": (C.c_int, [vp, vp, i64]),
     }
     for name, (res, args) in sigs.items():
+        if not hasattr(lib, name) and os.environ.get("AURORA_B200_AB_OLD_ABI"):
+            continue
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
+    if lib.aur_abi_version() != ABI_VERSION and not os.environ.get("AURORA_B200_AB_OLD_ABI"):   # (A/B runs against older builds)
+        raise NativeLibraryMissing(f"{LIB_PATH} has ABI version {lib.aur_abi_version()}, this binding needs {ABI_VERSION}: "
+                                   "rebuild it with `python -m aurora_b200.build --force`")
     _lib = lib
     return lib
 

@@ -29,7 +29,7 @@ def _model_config(name: str):
 def configure_from_env() -> None:
     from . import retriever
     from .encoder import Encoder, TextEncoder, from_hf_bert, read_safetensors
-    from .wordpiece import WordPieceTokenizer, load_vocab
+    from .wordpiece import NativeTokenizer
 
     missing = [v for v in ("AURORA_B200_ENCODER_WEIGHTS", "AURORA_B200_VOCAB") if not os.environ.get(v)]
     if missing:
@@ -40,11 +40,10 @@ def configure_from_env() -> None:
     enc = Encoder(cfg, max_tokens=int(os.environ.get("AURORA_B200_MAX_TOKENS", "32768")),
                   max_seqs=int(os.environ.get("AURORA_B200_MAX_SEQS", "2048")), device=device)
     enc.load_weights(from_hf_bert(read_safetensors(os.environ["AURORA_B200_ENCODER_WEIGHTS"]), cfg))
-    vocab = load_vocab(os.environ["AURORA_B200_VOCAB"])
-    if len(vocab) != cfg.vocab:
-        raise RuntimeError(f"vocabulary has {len(vocab)} entries, the model expects {cfg.vocab}")
-    tok = WordPieceTokenizer(vocab)
-    text_encoder = TextEncoder(enc, lambda t: tok.encode(t, max_len=cfg.max_pos))
+    tok = NativeTokenizer(os.environ["AURORA_B200_VOCAB"], lower=os.environ.get("AURORA_B200_CASED", "0") != "1")   # C++, multi-threaded
+    if tok.vocab_size != cfg.vocab:
+        raise RuntimeError(f"vocabulary has {tok.vocab_size} entries, the model expects {cfg.vocab}")
+    text_encoder = TextEncoder(enc, tok, max_len=cfg.max_pos)
     snap = os.environ.get("AURORA_B200_SNAPSHOT")
     if snap and os.path.exists(os.path.join(snap, "meta.json")):
         retriever.configure(factory=lambda: retriever.KnowledgeBase.load(snap, text_encoder, capacity=capacity, device=device))

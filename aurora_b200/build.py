@@ -14,8 +14,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libaurora_b200.so")
-SOURCES = ["capi.cu", "kernels_simt.cu", "simtopk_tc.cu", "encoder.cu", "encoder_simt.cu", "gemm_tc.cu", "attn_tc.cu"]
-HEADERS = ["internal.h", "ptx.cuh", os.path.join("..", "..", "include", "aurora_b200.h")]
+SOURCES = ["capi.cu", "kernels_simt.cu", "simtopk_tc.cu", "encoder.cu", "encoder_simt.cu", "gemm_tc.cu", "attn_tc.cu", "tokenizer.cpp"]
+HEADERS = ["internal.h", "ptx.cuh", "unicode_tables.inc", os.path.join("..", "..", "include", "aurora_b200.h")]
 
 PROFILE = bool(int(os.environ.get("AUR_TC_PROFILE", "0")))   # bring-up timers in the tcgen05 kernel
 EXTRA_DEFS = os.environ.get("AUR_EXTRA_DEFS", "").split()     # e.g. -DAUR_ATTN_POLY_EVERY=0 for an A/B build
@@ -52,7 +52,7 @@ def build_native(force: bool = False, verbose: bool = False, out: str = "", tag:
     nvcc = _nvcc()
     objs = []
     for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", (f".{tag}" if tag else "") + ".o"))
+        obj = os.path.join(CSRC, os.path.splitext(src)[0] + (f".{tag}" if tag else "") + ".o")
         cmd = [nvcc, *NVCC_FLAGS, *(["-DAUR_TC_PROFILE"] if PROFILE else []), *EXTRA_DEFS, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

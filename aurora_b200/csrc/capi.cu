@@ -114,7 +114,7 @@ struct SearchCtx {
   std::mutex mu;                  // one enqueue at a time
   cudaStream_t own_stream = nullptr;
   cudaStream_t bound = nullptr;   // caller stream this context serves (nullptr = pool context)
-  cudaEvent_t ev_begin = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_end = nullptr;
+  cudaEvent_t ev_begin = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_fin = nullptr, ev_end = nullptr;
   bool have_timing = false;
   int last_kernel = 0, last_launches = 0;
   int64_t snapshot_rows = 0;
@@ -136,6 +136,7 @@ struct SearchCtx {
     if (ev_begin) cudaEventDestroy(ev_begin);
     if (ev_k0) cudaEventDestroy(ev_k0);
     if (ev_k1) cudaEventDestroy(ev_k1);
+    if (ev_fin) cudaEventDestroy(ev_fin);
     if (ev_end) cudaEventDestroy(ev_end);
     if (own_stream) cudaStreamDestroy(own_stream);
   }
@@ -203,6 +204,7 @@ int ctx_init(aur_index* ix, SearchCtx* c) {
   CU_TRY(cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, hi));
   CU_TRY(cudaEventCreate(&c->ev_begin)); CU_TRY(cudaEventCreate(&c->ev_k0));
   CU_TRY(cudaEventCreate(&c->ev_k1));    CU_TRY(cudaEventCreate(&c->ev_end));
+  CU_TRY(cudaEventCreate(&c->ev_fin));
   (void)ix;
   return AUR_OK;
 }
@@ -389,6 +391,7 @@ int search_enqueue(aur_index* ix, SearchCtx* c, const void* q_dev, int nq, int k
     c->last_launches += 1;
   }
   if (!k_timed) { CU_TRY(cudaEventRecord(c->ev_k0, s)); CU_TRY(cudaEventRecord(c->ev_k1, s)); }
+  CU_TRY(cudaEventRecord(c->ev_fin, s));
   CU_TRY(cudaEventRecord(c->ev_end, s));
   c->have_timing = true;
   {
@@ -594,6 +597,8 @@ int aur_get_stats(aur_index* ix, aur_stats* out) {
       CU_TRY(cudaEventSynchronize(c->ev_end));
       CU_TRY(cudaEventElapsedTime(&out->last_kernel_ms, c->ev_k0, c->ev_k1));
       CU_TRY(cudaEventElapsedTime(&out->last_total_ms, c->ev_begin, c->ev_end));
+      CU_TRY(cudaEventElapsedTime(&out->last_finalize_ms, c->ev_k1, c->ev_fin));
+      CU_TRY(cudaEventElapsedTime(&out->last_merge_ms, c->ev_fin, c->ev_end));
     }
   }
   return AUR_OK;
@@ -615,6 +620,21 @@ int aur_export(aur_index* ix, void* rows_out, int64_t* ids_out, int32_t* user_ou
   if (user_out) CU_TRY(cudaMemcpy(user_out, ix->d_user, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
   if (org_out) CU_TRY(cudaMemcpy(org_out, ix->d_org, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
   for (int64_t i = 0; i < n; ++i) live_out[i] = inv[static_cast<size_t>(i)] == inv[static_cast<size_t>(i)];   // NaN = tombstone
+  return AUR_OK;
+}
+
+int aur_read_rows(aur_index* ix, int64_t row0, int64_t n, void* rows_out, int64_t* ids_out) {
+  if (!ix || (n > 0 && (!rows_out || !ids_out))) return fail(AUR_ERR_INVALID, "null argument");
+  std::shared_lock<std::shared_mutex> rl(ix->rw);
+  const int64_t rows = ix->rows_pub.load(std::memory_order_acquire);
+  if (row0 < 0 || n < 0 || row0 + n > rows) return fail(AUR_ERR_INVALID, "rows [%lld, %lld) are not inside the published prefix of %lld",
+                                                        (long long)row0, (long long)(row0 + n), (long long)rows);
+  if (n == 0) return AUR_OK;
+  CU_TRY(cudaSetDevice(ix->device));
+  const size_t rb = static_cast<size_t>(ix->dim) * ix->elt;
+  CU_TRY(cudaMemcpy(rows_out, static_cast<const uint8_t*>(ix->d_rows) + static_cast<size_t>(row0) * rb, static_cast<size_t>(n) * rb,
+                    cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(ids_out, ix->d_ids + row0, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost));
   return AUR_OK;
 }
 

@@ -169,7 +169,25 @@ finalize_kernel(FinalizeArgs a) {
   __shared__ double ex_score[kMaxK + kSlack];
   __shared__ int64_t ex_id[kMaxK + kSlack];
   __shared__ double s_qq;
+  __shared__ uint64_t topkeys[kMaxK + kSlack];
   const int qi = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  // ---- prologue, independent of the similarity kernel (launched with programmatic dependent launch, so this part
+  //      overlaps that kernel's tail): the query goes to shared memory once (as fp32, exact for bf16 / f32), |q|^2
+  const T* rows = static_cast<const T*>(a.rows);
+  const T* qv = static_cast<const T*>(a.q) + static_cast<size_t>(qi) * a.dim;
+  float* qs = reinterpret_cast<float*>(skeys + a.sort_cap);      // [dim] behind the sort buffer
+  for (int i = threadIdx.x; i < a.dim; i += blockDim.x) qs[i] = to_f32(qv[i]);
+  __syncthreads();
+  if (warp == 0) {
+    double qq = 0.0;
+    for (int i = lane; i < a.dim; i += 32) { const double v = static_cast<double>(qs[i]); qq = fma(v, v, qq); }
+    qq = warp_sum_lane0(qq);
+    if (lane == 0) s_qq = qq;
+  }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");     // the candidate lists come from the previous kernel
+
   const int cap = a.n_lists * a.ksel;                       // row stride of cand
   const int n = a.counts ? min(static_cast<int>(a.counts[qi]), cap) : cap;
   const uint64_t* src = a.cand + static_cast<size_t>(qi) * cap;
@@ -192,31 +210,17 @@ finalize_kernel(FinalizeArgs a) {
   __syncthreads();
   if (a.counts && threadIdx.x == 0) a.counts[qi] = 0;      // ready for the next launch
 
-  // Exact re-score.  The query goes to shared memory once (as fp32, exact for bf16 / f32);
-  // a warp takes one candidate: lanes stride over 16-byte pieces of the row, fp64 FMA, fixed
+  // Exact re-score: a warp takes one candidate: lanes stride over 16-byte pieces of the row, fp64 FMA, fixed
   // shuffle tree -- a row's score depends only on its content, never on where it is stored.
-  const T* rows = static_cast<const T*>(a.rows);
-  const T* qv = static_cast<const T*>(a.q) + static_cast<size_t>(qi) * a.dim;
-  float* qs = reinterpret_cast<float*>(skeys + a.sort_cap);      // [dim] behind the sort buffer
-  __shared__ uint64_t topkeys[kMaxK + kSlack];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int ncand = min(a.ksel, P);
   for (int c = threadIdx.x; c < ncand; c += blockDim.x) topkeys[c] = skeys[c];
-  for (int i = threadIdx.x; i < a.dim; i += blockDim.x) qs[i] = to_f32(qv[i]);
-  __syncthreads();
-  if (warp == 0) {
-    double qq = 0.0;
-    for (int i = lane; i < a.dim; i += 32) { const double v = static_cast<double>(qs[i]); qq = fma(v, v, qq); }
-    qq = warp_sum_lane0(qq);
-    if (lane == 0) s_qq = qq;
-  }
   __syncthreads();
   constexpr int kVec = 16 / static_cast<int>(sizeof(T));          // elements per 16-byte piece
   const bool vec_ok = (a.dim % kVec) == 0;
   // kRe candidates per warp and step, strided by the warp count, with every row load (and the id load)
-  // issued before any arithmetic: at k+slack = 40 and 16 warps all candidate rows of the query are in
+  // issued before any arithmetic: at k+slack = 40 and 8 warps x 5 all candidate rows of the query are in
   // flight at once, so the gather costs one HBM round trip instead of one per pass.
-  constexpr int kRe = 3, kMaxCh = 4;                                // rows per step; 16-byte pieces per lane (dim <= 1024 bf16)
+  constexpr int kRe = 5, kMaxCh = 4;                                // rows per step; 16-byte pieces per lane (dim <= 1024 bf16)
   const int n_chunks = vec_ok ? a.dim / kVec : 0;
   const bool reg_path = vec_ok && n_chunks <= 32 * kMaxCh;
   for (int c0 = warp; c0 < ncand; c0 += kRe * nwarps) {
@@ -518,9 +522,9 @@ cudaError_t launch_finalize(const FinalizeArgs& a_in, cudaStream_t s) {
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
   }
-  if (a.dtype == 0) finalize_kernel<__nv_bfloat16><<<a.nq, 256, smem, s>>>(a);
-  else finalize_kernel<float><<<a.nq, 256, smem, s>>>(a);
-  return cudaGetLastError();
+  // programmatic dependent launch: blocks start (query -> shared memory, |q|^2) while the similarity kernel drains
+  if (a.dtype == 0) return launch_pdl(finalize_kernel<__nv_bfloat16>, dim3(a.nq), dim3(256), smem, s, 1, a);
+  return launch_pdl(finalize_kernel<float>, dim3(a.nq), dim3(256), smem, s, 1, a);
 }
 
 cudaError_t launch_merge_topk(const double* in_s, const int64_t* in_ids, size_t shard_stride, int n_shards, int nq, int k,

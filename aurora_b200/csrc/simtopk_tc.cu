@@ -64,11 +64,12 @@ using namespace ptx;
 namespace {
 
 constexpr int kThrWarps = 1;
+constexpr int kQStageBufs = 2;   // ring stages (the last ones) the query load borrows as its transpose buffer
 constexpr uint32_t kSlot = kTcQRows * 8u;   // byte stride between list slots of one query
 
 struct SmemLayout {
   uint32_t stage_bytes, box_bytes, lcap, fifo_recs, qs_kb;
-  uint32_t off_qs, off_list, off_norm, off_fifo, off_bar, total;
+  uint32_t off_qs, off_list, off_norm, off_fifo, off_tau, off_bar, total;
 };
 __host__ __device__ inline SmemLayout make_layout(int cta_group, int epi_groups, int num_stages, int ksel, int dim) {
   SmemLayout L;
@@ -85,7 +86,8 @@ __host__ __device__ inline SmemLayout make_layout(int cta_group, int epi_groups,
   // deferred-candidate FIFO: per thread kTcFifoRecs records of four adjacent scores (16 B) + a row tag
   L.fifo_recs = (epi_groups == 1 && ksel <= kTcFifoMaxKsel) ? kTcFifoRecs : 0u;
   L.off_fifo = o;   o += L.fifo_recs * kTcQRows * (16u + 4u);
-  L.off_bar = o;    o += (2u * kTcMaxStages + 2u + 2u + 1u) * 8u + 16u;
+  L.off_tau = o;    o += kTcQRows * 4u;   // certified thresholds of this CTA's 128 queries, refreshed by the threshold warp
+  L.off_bar = o;    o += (2u * kTcMaxStages + 2u + 2u + 2u) * 8u + 16u;
   L.total = o;
   return L;
 }
@@ -189,16 +191,23 @@ __device__ __noinline__ TopkState drain_fifo(TopkState st, uint32_t fifo_a, uint
 // Warp-cooperative: R-th largest of the values published for one query by up to 96 CTAs
 // (lane i holds entries i, i+32, i+64; entries of other launches or not yet written are
 // skipped).  Bisection on the value with ballot counts.  Returns -inf when fewer than R CTAs
-// have published.  All lanes return the same value.
-__device__ float exchange_threshold_warp(const unsigned long long* pubrow, int nuse, int R, uint32_t epoch, int lane) {
+// have published.  All lanes return the same value.  The three entries are loaded by the caller
+// (exchange_load) so that several rows' loads can be in flight before any is consumed.
+struct PubEntries { unsigned long long e[3]; };
+__device__ __forceinline__ PubEntries exchange_load(const unsigned long long* pubrow, int nuse, int lane) {
+  PubEntries r;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { const int i = lane + 32 * k; r.e[k] = (i < nuse) ? __ldcg(pubrow + i) : 0ull; }
+  return r;
+}
+__device__ float exchange_select(const PubEntries& ent, int nuse, int R, uint32_t epoch, int lane) {
   float v[3];
   float lo = INFINITY, hi = -INFINITY;
   int nvalid = 0;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const int i = lane + 32 * k;
-    unsigned long long e = 0ull;
-    if (i < nuse) e = __ldcg(pubrow + i);
+    const unsigned long long e = ent.e[k];
     const bool ok = (i < nuse) && static_cast<uint32_t>(e >> 32) == epoch;
     v[k] = ok ? ord_to_f32(static_cast<uint32_t>(e)) : __int_as_float(0x7FC00000);
     nvalid += __popc(__ballot_sync(0xffffffffu, ok));
@@ -243,13 +252,15 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
 
   const SmemLayout L = make_layout(kCtaGroup, kEpiGroups, p.num_stages, p.ksel, p.dim);
   float* normbuf = reinterpret_cast<float*>(smem + L.off_norm);      // [4 warps][2][64]
+  volatile float* tau_s = reinterpret_cast<volatile float*>(smem + L.off_tau);   // [128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);
   uint64_t* full_bar = bars;                              // [kTcMaxStages]
   uint64_t* empty_bar = bars + kTcMaxStages;              // [kTcMaxStages]
   uint64_t* tmem_full = bars + 2 * kTcMaxStages;          // [2]
   uint64_t* tmem_empty = bars + 2 * kTcMaxStages + 2;     // [2]
   uint64_t* q_ready = bars + 2 * kTcMaxStages + 4;        // [1]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kTcMaxStages + 5);
+  uint64_t* q_staged = bars + 2 * kTcMaxStages + 5;       // [1] local: the query load no longer uses ring stages as scratch
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kTcMaxStages + 6);
   volatile int* epi_done = reinterpret_cast<volatile int*>(tmem_ptr_smem + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -291,28 +302,43 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       mbar_init(&tmem_empty[i], 4 * kCtaGroup);          // the four warps (per CTA) that drain this buffer
     }
     mbar_init(q_ready, kEpiWarps * kCtaGroup);
+    mbar_init(q_staged, kEpiWarps);
     *epi_done = 0;
     fence_mbar_init();
   } else if (warp == kProducerWarp) {
     tmem_alloc<kCtaGroup>(tmem_ptr_smem, 512);
     tmem_relinquish<kCtaGroup>();
+  } else if (warp < kThrWarps) {
+    for (int i = lane; i < kTcQRows; i += 32) tau_s[i] = -INFINITY;
   }
   tc_fence_before();
   if constexpr (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  grid_dep_launch();   // the exact re-rank kernel behind this one may start its prologue as CTAs here retire
 
   if (warp == kProducerWarp) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
       const uint64_t hint = (kCtaGroup == 2 || p.n_qblocks == 1) ? kEvictFirst : kEvictNormal;
       int stage = 0; uint32_t phase = 0;
+      bool q_done = p.num_stages < 2 * kQStageBufs;   // too few stages: the query load does not borrow any
+      long long tp_wait = 0;
+      const long long tp_begin = TCLK();
+#ifdef AUR_TC_PROFILE
+      unsigned long long gt0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
+#endif
       for (int it = 0; it < my_tiles; ++it) {
         const int tile = tset + it * n_tsets;
         const int row0 = tile * kTcTileN + static_cast<int>(rank) * (kTcTileN / kCtaGroup);
         for (int kb0 = 0; kb0 < kbs; kb0 += kTcKbPerStage) {
           const int nkb = min(kTcKbPerStage, kbs - kb0);
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (!q_done && stage >= p.num_stages - kQStageBufs) { mbar_wait(q_staged, 0); q_done = true; }   // (see the query load)
+          {
+            const long long t0 = TCLK();
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            tp_wait += TCLK() - t0;
+          }
           uint8_t* dst = smem + static_cast<uint32_t>(stage) * L.stage_bytes;
           if constexpr (kCtaGroup == 1) {
             mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(nkb) * L.box_bytes);
@@ -327,6 +353,14 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
           if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
         }
       }
+#ifdef AUR_TC_PROFILE
+      if ((p.dbg_flags & 64) && p.dbg_scores != nullptr) {
+        unsigned long long gt1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+        float* d = p.dbg_scores + static_cast<size_t>(blockIdx.x) * kTcQRows * kTcTileN + 36;
+        d[0] = static_cast<float>(tp_wait); d[1] = static_cast<float>(TCLK() - tp_begin);
+        d[2] = static_cast<float>(gt1 - gt0);     // ns: cycles / ns = the SM clock the kernel really ran at
+      }
+#endif
     }
   } else if (warp == kMmaWarp) {
     // ============================== MMA issuer ==============================
@@ -414,17 +448,39 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       // ============================== threshold warp ==============================
       // Serve the queries r = tset, tset + n_tsets, ... of this CTA's query block.
       float cur[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      int polls = 0;
       while (xchg && my_tiles > 0) {
-        __nanosleep(1500);
+        // every epilogue thread of the grid waits for the FIRST threshold (bootstrap): poll fast until it is out
+        __nanosleep(polls < 48 ? 150 : 1500);
+        ++polls;
         const bool done = *epi_done >= kEpiWarps;
-        int slot = 0;
-        for (int rq = tset; rq < kTcQRows && slot < 4; rq += n_tsets, ++slot) {
-          const float t = exchange_threshold_warp(pub_base + static_cast<size_t>(rq) * pub_stride, nuse, xR, p.epoch, lane);
-          if (t > cur[slot]) {
-            cur[slot] = t;
-            if (lane == 0) __stcg(thr_base + rq, (static_cast<unsigned long long>(p.epoch) << 32) | __float_as_uint(t));
+        // every global load of this round is issued before the first one is consumed: one L2 round trip per round
+        unsigned long long cached[kTcQRows / 32];
+#pragma unroll
+        for (int j = 0; j < kTcQRows / 32; ++j) cached[j] = __ldcg(thr_base + j * 32 + lane);
+        PubEntries ent[4];
+        int nslot = 0;
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+          const int rq = tset + sl * n_tsets;
+          if (rq < kTcQRows) { ent[sl] = exchange_load(pub_base + static_cast<size_t>(rq) * pub_stride, nuse, lane); nslot = sl + 1; }
+        }
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+          if (sl < nslot) {
+            const int rq = tset + sl * n_tsets;
+            const float t = exchange_select(ent[sl], nuse, xR, p.epoch, lane);
+            if (t > cur[sl]) {
+              cur[sl] = t;
+              if (lane == 0) __stcg(thr_base + rq, (static_cast<unsigned long long>(p.epoch) << 32) | __float_as_uint(t));
+            }
           }
         }
+        // Refresh this CTA's cache of its 128 queries' certified thresholds.  The epilogue reads them from shared
+        // memory once per tile; a global (L2) read there sat on the per-tile critical path with its full latency.
+#pragma unroll
+        for (int j = 0; j < kTcQRows / 32; ++j)
+          if (static_cast<uint32_t>(cached[j] >> 32) == p.epoch) tau_s[j * 32 + lane] = __uint_as_float(static_cast<uint32_t>(cached[j]));   // only ever rises
         if (done) break;
       }
     } else {
@@ -434,32 +490,95 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       // ---- park this thread's query row in TMEM (bf16 pairs, K ascending along columns);
       //      with two groups each loads every other k-block
       {
-        const uint4* src = reinterpret_cast<const uint4*>(p.q + static_cast<size_t>(qglob) * p.dim);
-        for (int kb = grp; kb < kbs; kb += kEpiGroups) {
-          uint32_t v[2][16];
+        // A thread needs ITS row (TMEM lane = query), but 32 lanes reading 32 different rows cost 32 L1 wavefronts per
+        // load instruction -- 14k cycles for the block.  So a warp reads its 32 rows coalesced (lane l takes 16-byte
+        // piece l of 4 consecutive rows per instruction), transposes through shared memory -- borrowed from the last
+        // ring stages, which the TMA producer leaves alone until q_staged completes -- and every lane reads its own
+        // row back.  Staging layout = the 128-byte-swizzled K-major tile TMA would produce, so dims past 768 (which
+        // stay in shared memory as the SS-MMA operand) are written straight to their final place.
+        const bool staged = p.num_stages >= 2 * kQStageBufs;
+        const int ew = warp - kThrWarps;                      // epilogue warp 0 .. 4G-1
+        constexpr int kBufs = (kEpiGroups == 1) ? 2 : 1;      // 4 KB transpose buffers per warp
+        uint8_t* stg = smem + static_cast<uint32_t>(p.num_stages - kQStageBufs) * L.stage_bytes + ew * (kBufs * 4096);
+        const uint8_t* qbase = reinterpret_cast<const uint8_t*>(p.q);
+        const size_t row_bytes = static_cast<size_t>(p.dim) * 2;
+        const int wrow0 = qblock * kTcQRows + quarter * 32;   // first query of this warp
+        auto load_kb = [&](int kb, uint4 (&x)[8]) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            uint4 x = make_uint4(0, 0, 0, 0);
-            if (qglob < p.nq) x = ldg_nc_v4(src + kb * 8 + i);
-            v[i >> 2][(i & 3) * 4 + 0] = x.x; v[i >> 2][(i & 3) * 4 + 1] = x.y;
-            v[i >> 2][(i & 3) * 4 + 2] = x.z; v[i >> 2][(i & 3) * 4 + 3] = x.w;
+            const int id = i * 32 + lane, row = id >> 3, c = id & 7;
+            x[i] = make_uint4(0, 0, 0, 0);
+            if (kb < kbs && wrow0 + row < p.nq) x[i] = ldg_nc_v4(qbase + static_cast<size_t>(wrow0 + row) * row_bytes + kb * 128 + c * 16);
           }
-          if (kb < kTcTmemDim / kTcKBlock) {
-            tmem_st_x16(lane_addr + kb * 32, v[0]);
-            tmem_st_x16(lane_addr + kb * 32 + 16, v[1]);
-          } else {   // K-major tile with the 128-byte swizzle TMA would have produced: 16-byte chunk c of row r at c ^ (r & 7)
-            uint8_t* qrow = smem + L.off_qs + static_cast<uint32_t>(kb - kTcTmemDim / kTcKBlock) * (kTcQRows * 128u) + r * 128u;
+        };
+        auto scatter_kb = [&](uint8_t* tile, const uint4 (&x)[8]) {   // tile: this warp's [32 rows x 128 B], swizzled
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              *reinterpret_cast<uint4*>(qrow + ((c ^ (r & 7)) << 4)) =
-                  make_uint4(v[c >> 2][(c & 3) * 4 + 0], v[c >> 2][(c & 3) * 4 + 1], v[c >> 2][(c & 3) * 4 + 2], v[c >> 2][(c & 3) * 4 + 3]);
+          for (int i = 0; i < 8; ++i) {
+            const int id = i * 32 + lane, row = id >> 3, c = id & 7;
+            *reinterpret_cast<uint4*>(tile + row * 128 + ((c ^ (row & 7)) << 4)) = x[i];
+          }
+        };
+        if (staged) {
+          // every CTA pair reads the same 256 x dim block at the same moment: start each pair at a different
+          // k-block (rotation by tile set) so they do not all queue on the same L2 lines
+          const int n_j = (kbs - grp + kEpiGroups - 1) / kEpiGroups;      // k-blocks this group loads
+          const int rot = n_j > 0 ? tset % n_j : 0;
+          auto kb_of = [&](int j) { return (j < n_j) ? grp + ((j + rot) % n_j) * kEpiGroups : kbs; };
+          uint4 xa[8], xb[8];
+          load_kb(kb_of(0), xa);
+          for (int j = 0; j < n_j; ++j) {
+            const int kb = kb_of(j);
+            load_kb(kb_of(j + 1), xb);                        // next k-block in flight
+            if (kb < kTcTmemDim / kTcKBlock) {
+              uint8_t* buf = stg + (j % kBufs) * 4096;
+              if (kBufs == 1) __syncwarp();
+              scatter_kb(buf, xa);
+              __syncwarp();
+              uint32_t v[2][16];
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const uint4 t = *reinterpret_cast<const uint4*>(buf + lane * 128 + ((c ^ (lane & 7)) << 4));
+                v[c >> 2][(c & 3) * 4 + 0] = t.x; v[c >> 2][(c & 3) * 4 + 1] = t.y;
+                v[c >> 2][(c & 3) * 4 + 2] = t.z; v[c >> 2][(c & 3) * 4 + 3] = t.w;
+              }
+              tmem_st_x16(lane_addr + kb * 32, v[0]);
+              tmem_st_x16(lane_addr + kb * 32 + 16, v[1]);
+            } else {
+              scatter_kb(smem + L.off_qs + static_cast<uint32_t>(kb - kTcTmemDim / kTcKBlock) * (kTcQRows * 128u) + quarter * 32 * 128, xa);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) xa[i] = xb[i];
+          }
+        } else {   // hardly any ring (large k at dim > 768): every thread fetches its own row
+          const uint4* src = reinterpret_cast<const uint4*>(p.q + static_cast<size_t>(qglob) * p.dim);
+          for (int kb = grp; kb < kbs; kb += kEpiGroups) {
+            uint32_t v[2][16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              uint4 x = make_uint4(0, 0, 0, 0);
+              if (qglob < p.nq) x = ldg_nc_v4(src + kb * 8 + i);
+              v[i >> 2][(i & 3) * 4 + 0] = x.x; v[i >> 2][(i & 3) * 4 + 1] = x.y;
+              v[i >> 2][(i & 3) * 4 + 2] = x.z; v[i >> 2][(i & 3) * 4 + 3] = x.w;
+            }
+            if (kb < kTcTmemDim / kTcKBlock) {
+              tmem_st_x16(lane_addr + kb * 32, v[0]);
+              tmem_st_x16(lane_addr + kb * 32 + 16, v[1]);
+            } else {   // K-major tile with the 128-byte swizzle TMA would have produced: 16-byte chunk c of row r at c ^ (r & 7)
+              uint8_t* qrow = smem + L.off_qs + static_cast<uint32_t>(kb - kTcTmemDim / kTcKBlock) * (kTcQRows * 128u) + r * 128u;
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<uint4*>(qrow + ((c ^ (r & 7)) << 4)) =
+                    make_uint4(v[c >> 2][(c & 3) * 4 + 0], v[c >> 2][(c & 3) * 4 + 1], v[c >> 2][(c & 3) * 4 + 2], v[c >> 2][(c & 3) * 4 + 3]);
+            }
           }
         }
         tmem_wait_st();
-        fence_proxy_async_smem();   // (shared-memory part of the queries -> visible to the tensor core)
+        fence_proxy_async_smem();   // (shared-memory part of the queries -> visible to the tensor core; the borrowed
+                                    //  ring stages -> safe for TMA to overwrite)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
+          mbar_arrive(q_staged);
           if constexpr (kCtaGroup == 2) mbar_arrive_cluster(q_ready, 0); else mbar_arrive(q_ready);
         }
       }
@@ -528,8 +647,8 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         const long long tb = clock64();
         float tboot = -INFINITY;
         do {
-          __nanosleep(300);
-          tboot = read_threshold(thr_q, p.epoch);
+          __nanosleep(100);
+          tboot = tau_s[r];
         } while (__any_sync(0xffffffffu, tboot == -INFINITY) && clock64() - tb < 100000);
         st.tau = fmaxf(st.tau, tboot);
         t_boot = TCLK() - t_begin;
@@ -542,7 +661,7 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         const int b = it & 1;
         const float* nb = mynorm + (li & 1) * kTcTileN;
         const long long t_top0 = TCLK();
-        const unsigned long long thr_e = (xchg && !(p.dbg_flags & 16)) ? __ldcg(thr_q) : 0ull;   // consumed after the fast path
+        const float thr_now = (xchg && !(p.dbg_flags & 16)) ? tau_s[r] : -INFINITY;   // shared-memory copy kept by the threshold warp
 
         // norms of the next tile (loaded one iteration ago) -> the other buffer; start the
         // loads for the tile after that.  A whole tile period hides the HBM latency.
@@ -606,7 +725,7 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         if (p.dbg_flags & 8) { st.top1 = fmaxf(st.top1, fmaxf(fmaxf(cmax[0], cmax[1]), fmaxf(cmax[2], cmax[3]))); continue; }
         const long long t_ch0 = TCLK();
         // A group of four scores whose max reaches this query's threshold goes out of line.
-        if (static_cast<uint32_t>(thr_e >> 32) == p.epoch) st.tau = fmaxf(st.tau, __uint_as_float(static_cast<uint32_t>(thr_e)));
+        st.tau = fmaxf(st.tau, thr_now);
         if (use_fifo) {
           st.top1 = fmaxf(st.top1, fmaxf(fmaxf(cmax[0], cmax[1]), fmaxf(cmax[2], cmax[3])));   // published below
 #pragma unroll

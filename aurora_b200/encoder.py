@@ -153,30 +153,102 @@ class Encoder:
 
 
 class TextEncoder:
-    """Adapter for aurora_b200.retriever.KnowledgeBase: ``dim`` + ``encode(texts)`` over a tokenizer
-    callable and the CUDA ``Encoder``; ``encode_append`` is the fused ingest path (vectors never
-    leave the device between the forward pass and the shard append)."""
+    """Adapter for aurora_b200.retriever.KnowledgeBase: ``dim`` + ``encode(texts)`` over a tokenizer and the CUDA
+    ``Encoder``; ``encode_append`` is the fused ingest path (vectors never leave the device between the forward
+    pass and the shard append).
 
-    def __init__(self, encoder: Encoder, tokenize: Callable[[str], List[int]]):
-        self._enc, self._tok = encoder, tokenize
+    ``tokenizer``: an ``aurora_b200.wordpiece.NativeTokenizer`` (C++, multi-threaded -- then whole batches go through
+    ONE C call, ``aur_encode_text_append``, with no Python per text) or any ``tokenize(text) -> list[int]`` callable.
+
+    Texts longer than the position table (the reference's chunker can emit a 4 000-character chunk,
+    document_processor.py:266-267) are not cut off: they are split into windows of ``max_pos`` tokens, each window is
+    encoded, and the text's vector is the L2-normalised mean of its windows -- the same idea as the t2v sidecar's
+    sentence batching + averaging (that container's exact splitting rule is not in the reference tree)."""
+
+    def __init__(self, encoder: Encoder, tokenizer, max_len: Optional[int] = None):
+        self._enc, self._tok = encoder, tokenizer
+        self._native = hasattr(tokenizer, "encode_packed")
         self.dim = encoder.cfg.hidden
+        self.max_len = int(max_len or encoder.cfg.max_pos)
 
+    # ------------------------------------------------------------------ tokenisation
+    def _tokenize(self, texts: Sequence[str], max_len: int):
+        if self._native:
+            return self._tok.encode_packed(list(texts), max_len)
+        seqs = []
+        for t in texts:
+            ids = list(self._tok(t))
+            seqs.append(ids if len(ids) <= max_len else ids[: max_len - 1] + ids[-1:])
+        return pack_sequences(seqs)
+
+    def _windows(self, text: str):
+        """Token windows of one over-long text: [CLS] body[i : i + max_len - 2] [SEP]."""
+        tok, cu = self._tokenize([text], 1 << 20) if self._native else pack_sequences([list(self._tok(text))])
+        ids = tok[cu[0]:cu[1]]
+        cls, sep, body = ids[0], ids[-1], ids[1:-1]
+        step = self.max_len - 2
+        return [np.concatenate(([cls], body[i:i + step], [sep])).astype(np.int32) for i in range(0, max(len(body), 1), step)]
+
+    def _encode_packed_any(self, tok: np.ndarray, cu: np.ndarray) -> np.ndarray:
+        out = np.empty((len(cu) - 1, self.dim), dtype=np.float32)
+        i = 0
+        while i < len(cu) - 1:
+            j = i
+            while j < len(cu) - 1 and j - i < self._enc.max_seqs and cu[j + 1] - cu[i] <= self._enc.max_tokens:
+                j += 1
+            if j == i:
+                raise ValueError(f"text {i} tokenizes to {cu[i + 1] - cu[i]} tokens: more than max_tokens={self._enc.max_tokens}")
+            out[i:j] = self._enc.encode_packed(tok[cu[i]:cu[j]], (cu[i:j + 1] - cu[i]).astype(np.int32))
+            i = j
+        return out
+
+    def _encode_long(self, text: str) -> np.ndarray:
+        wins = self._windows(text)
+        tok, cu = pack_sequences(wins)
+        v = self._encode_packed_any(tok, cu).mean(axis=0)
+        n = float(np.linalg.norm(v))
+        return v / n if (self._enc.cfg.normalize and n > 0) else v
+
+    # ------------------------------------------------------------------ API used by the retriever
     def encode(self, texts: Sequence[str]) -> np.ndarray:
-        return self._enc.encode([self._tok(t) for t in texts])
+        tok, cu = self._tokenize(texts, self.max_len)
+        out = self._encode_packed_any(tok, cu)
+        for i in np.nonzero(np.diff(cu) >= self.max_len)[0]:          # possibly truncated: look again without the limit
+            if len(self._windows(texts[i])) > 1:
+                out[i] = self._encode_long(texts[i])
+        return out
 
     def encode_append(self, index, texts: Sequence[str], ids: np.ndarray, user_codes=None, org_codes=None) -> None:
-        seqs = [self._tok(t) for t in texts]
-        i = 0
-        while i < len(seqs):
-            j, toks = i, 0
-            while j < len(seqs) and j - i < self._enc.max_seqs and toks + len(seqs[j]) <= self._enc.max_tokens:
-                toks += len(seqs[j]); j += 1
-            if j == i:
-                raise ValueError(f"text {i} tokenizes to {len(seqs[i])} tokens: more than max_tokens={self._enc.max_tokens}")
-            tok, cu = pack_sequences(seqs[i:j])
-            self._enc.encode_append(index, tok, cu, ids[i:j], None if user_codes is None else user_codes[i:j],
-                                    None if org_codes is None else org_codes[i:j])
-            i = j
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        tok, cu = self._tokenize(texts, self.max_len)
+        long_ones = [int(i) for i in np.nonzero(np.diff(cu) >= self.max_len)[0] if len(self._windows(texts[int(i)])) > 1]
+        short = [i for i in range(len(texts)) if i not in set(long_ones)]
+        u = None if user_codes is None else np.ascontiguousarray(user_codes, dtype=np.int32)
+        o = None if org_codes is None else np.ascontiguousarray(org_codes, dtype=np.int32)
+        if short:
+            if self._native and not long_ones:
+                self._append_texts_native(index, texts, ids, u, o)
+            else:
+                seqs = [tok[cu[i]:cu[i + 1]] for i in short]
+                sel = np.asarray(short)
+                i = 0
+                while i < len(seqs):
+                    j, toks = i, 0
+                    while j < len(seqs) and j - i < self._enc.max_seqs and toks + len(seqs[j]) <= self._enc.max_tokens:
+                        toks += len(seqs[j]); j += 1
+                    if j == i:
+                        raise ValueError(f"text {short[i]} tokenizes to {len(seqs[i])} tokens: more than max_tokens={self._enc.max_tokens}")
+                    t, c = pack_sequences(seqs[i:j])
+                    self._enc.encode_append(index, t, c, ids[sel[i:j]], None if u is None else u[sel[i:j]], None if o is None else o[sel[i:j]])
+                    i = j
+        for i in long_ones:                                           # averaged windows: the vector is formed on the host
+            v = self._encode_long(texts[i])[None, :]
+            index.add(v, ids[i:i + 1], None if u is None else u[i:i + 1], None if o is None else o[i:i + 1])
+
+    def _append_texts_native(self, index, texts, ids, u, o) -> None:
+        blob, offs = self._tok._pack(list(texts))
+        N.check(self._enc._lib.aur_encode_text_append(self._enc._h, self._tok._h, index._h, blob, _ptr(offs), len(texts), self.max_len,
+                                                      self._enc.max_tokens, self._enc.max_seqs, _ptr(ids), _ptr(u), _ptr(o), 0))
 
 
 # ----------------------------------------------------------------------------- reference mirror

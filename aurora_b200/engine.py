@@ -141,6 +141,13 @@ class Index:
         N.check(self._lib.aur_search_ex(self._h, _ptr(q), nq, int(k), None, None, _ptr(scores), _ptr(ids), C.byref(snap)))
         return ids, scores, int(snap.value)
 
+    def read_rows(self, row0: int, n: int):
+        """(rows [n, dim] uint16 bf16 bits or float32, ids [n]) of appended rows row0 .. row0 + n."""
+        rows = np.empty((n, self.dim), dtype=np.uint16 if self.dtype == N.AUR_BF16 else np.float32)
+        ids = np.empty(n, dtype=np.int64)
+        N.check(self._lib.aur_read_rows(self._h, int(row0), int(n), _ptr(rows), _ptr(ids)))
+        return rows, ids
+
     def compact(self) -> int:
         """Reclaim tombstoned rows (exclusive; waits for searches in flight).  Returns the rows freed."""
         freed = C.c_int64(0)

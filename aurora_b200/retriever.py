@@ -163,7 +163,8 @@ class KnowledgeBase:
 
     # ------------------------------------------------------------------ search
     def query(self, query: str, limit: int, filters=None, user_id: Optional[str] = None,
-              org_id: Optional[str] = None, alpha: Optional[float] = None, scoped: bool = False) -> List[SimpleNamespace]:
+              org_id: Optional[str] = None, alpha: Optional[float] = None, scoped: bool = False,
+              _dense: Optional[List[Tuple[int, float]]] = None) -> List[SimpleNamespace]:
         """Top-``limit`` objects.  ``alpha`` None or >= 1: pure vector search, ``score`` = cosine
         (near_text, incident_feedback/weaviate_client.py:286-297).  ``alpha`` < 1: hybrid with ranked
         fusion (weaviate_client.py:252-259): dense and BM25 lists fused as alpha/(rank+60) +
@@ -183,7 +184,7 @@ class KnowledgeBase:
             return []
         hybrid = alpha is not None and alpha < 1.0
         dense_w = 1.0 if not hybrid else max(0.0, float(alpha))
-        qv = self.encoder.encode([query]) if dense_w > 0.0 else None
+        qv = self.encoder.encode([query]) if (dense_w > 0.0 and _dense is None) else None
         with self._lock:
             tenant = scoped or user_id is not None or org_id is not None
 
@@ -208,7 +209,9 @@ class KnowledgeBase:
                 allowed = [rid for rid in cand if filters.matches(self._props[rid]) and tenant_ok(self._props[rid])]
 
             dense: List[Tuple[int, float]] = []
-            if qv is not None and (allowed is None or allowed):
+            if _dense is not None:          # dense leg already computed by query_batch (same scope, same fetch)
+                dense = [(rid, sc) for rid, sc in _dense if rid in self._props]
+            elif qv is not None and (allowed is None or allowed):
                 fetch = max(1, min(_MAX_FETCH, limit if not hybrid else _MAX_FETCH))
                 if allowed is not None:
                     ids, scores = self.index.search_subset(qv, fetch, np.asarray(allowed, dtype=np.int64))
@@ -247,6 +250,32 @@ class KnowledgeBase:
                 meta = SimpleNamespace(score=float(score), distance=None if cosine is None else 1.0 - float(cosine))
                 out.append(SimpleNamespace(properties=dict(self._props[rid]), uuid=self._id2key.get(rid), metadata=meta))
             return out
+
+    def query_batch(self, reqs: List[Tuple[Optional[str], str, int, Optional[float], Optional[str]]]) -> List[List[SimpleNamespace]]:
+        """Several tenant-scoped searches at once: ``(user_id, query, limit, alpha, org_id)`` each.  All query texts go
+        through ONE encoder batch; the dense leg runs as one kernel launch per distinct tenant scope (a uniform scope
+        folds into the row scale, so the tensor-core kernel serves it); fusion / shaping per request as in ``query``."""
+        need = [i for i, (u, q, lim, a, o) in enumerate(reqs) if lim > 0 and (u or o) and (a is None or a > 0.0)]
+        vecs = self.encoder.encode([reqs[i][1] for i in need]) if need else None
+        dense: Dict[int, List[Tuple[int, float]]] = {}
+        with self._lock:
+            groups: Dict[Tuple[int, int, int], List[int]] = {}
+            for pos, i in enumerate(need):
+                u, _, lim, a, o = reqs[i]
+                hybrid = a is not None and a < 1.0
+                fetch = max(1, min(_MAX_FETCH, lim if not hybrid else _MAX_FETCH))
+                cu = self._code(self._user_code, u, False) if u else -2
+                co = self._code(self._org_code, o, False) if o else -1
+                groups.setdefault((cu, -1 if co == -2 else co, fetch), []).append(pos)
+            for (cu, co, fetch), members in groups.items():
+                q = vecs[members]
+                ids, scores = self.index.search(q, fetch, np.full(len(members), cu, np.int32), np.full(len(members), co, np.int32))
+                for row, pos in enumerate(members):
+                    dense[need[pos]] = [(int(r), float(s_)) for r, s_ in zip(ids[row], scores[row]) if r >= 0]
+        out = []
+        for i, (u, q, lim, a, o) in enumerate(reqs):
+            out.append(self.query(q, lim, user_id=u, org_id=o, alpha=a, scoped=True, _dense=dense.get(i)))
+        return out
 
     # ------------------------------------------------------------------ persistence
     def save(self, directory: str) -> None:
@@ -445,6 +474,37 @@ def search_knowledge_base(user_id: str, query: str, limit: int = 5, alpha: float
     except Exception as e:
         logger.error(f"[KB B200] Error searching: {e}")
         return []
+
+
+def _shape_results(objs, min_score: float) -> List[Dict[str, Any]]:
+    results = []
+    for obj in objs:
+        score = obj.metadata.score if obj.metadata else 0.0
+        if min_score > 0.0 and score < min_score:
+            continue
+        p = obj.properties
+        results.append({"content": p.get("content", ""), "heading_context": p.get("heading_context", ""),
+                        "source_filename": p.get("source_filename", ""), "document_id": p.get("document_id", ""),
+                        "chunk_index": p.get("chunk_index", 0), "score": score})
+    return results
+
+
+def search_knowledge_base_batch(requests: List[Tuple]) -> List[List[Dict[str, Any]]]:
+    """Several ``search_knowledge_base`` calls answered together -- ``(user_id, query, limit, alpha, min_score, org_id)``
+    each, same result per element as the single call (weaviate_client.py:215-285).  The engine daemon coalesces the
+    concurrent calls of the reference's gunicorn threads into this (one encoder batch, one launch per tenant scope)."""
+    out: List[List[Dict[str, Any]]] = [[] for _ in requests]
+    live = [i for i, r in enumerate(requests) if isinstance(r[1], str) and r[1].strip()]
+    if not live:
+        return out
+    try:
+        reqs = [(requests[i][0], requests[i][1], requests[i][2], requests[i][3], requests[i][5]) for i in live]
+        for i, objs in zip(live, _get_kb().query_batch(reqs)):
+            out[i] = _shape_results(objs, requests[i][4])
+    except Exception as e:
+        logger.error(f"[KB B200] Error in batched search: {e}")
+        return [[] for _ in requests]
+    return out
 
 
 def delete_document_chunks(user_id: str, document_id: str) -> int:

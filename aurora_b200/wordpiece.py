@@ -112,3 +112,74 @@ class WordPieceTokenizer:
 
     def encode_batch(self, texts: Iterable[str], max_len: int = 512) -> List[List[int]]:
         return [self.encode(t, max_len) for t in texts]
+
+
+class NativeTokenizer:
+    """The same tokenisation in C++ behind the C ABI (csrc/tokenizer.cpp, ``aur_tokenize``): multi-threaded, GIL-free,
+    ids identical to ``transformers.BertTokenizer``.  This is what the ingest path uses; the pure-Python class above
+    stays as the readable restatement the tests cross-check it with.
+
+    ``vocab``: path of a vocab.txt, or a ``{piece: id}`` dict / list of pieces (ids must be 0..n-1)."""
+
+    def __init__(self, vocab, lower: bool = True):
+        import ctypes as C
+
+        from . import _native as N
+
+        self._N, self._lib, self._h = N, N.load(), C.c_void_p()
+        if isinstance(vocab, (str, bytes)):
+            path = vocab if isinstance(vocab, bytes) else vocab.encode()
+            N.check(self._lib.aur_tokenizer_open(path, int(lower), C.byref(self._h)))
+        else:
+            pieces = list(vocab) if not isinstance(vocab, dict) else [p for p, _ in sorted(vocab.items(), key=lambda kv: kv[1])]
+            if isinstance(vocab, dict) and sorted(vocab.values()) != list(range(len(vocab))):
+                raise ValueError("vocabulary ids must be 0 .. n-1")
+            blob = "\n".join(pieces).encode("utf-8")
+            N.check(self._lib.aur_tokenizer_open_mem(blob, len(blob), int(lower), C.byref(self._h)))
+        vs, unk, cls, sep = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        N.check(self._lib.aur_tokenizer_info(self._h, C.byref(vs), C.byref(unk), C.byref(cls), C.byref(sep)))
+        self.vocab_size, self.unk_id, self.cls_id, self.sep_id = vs.value, unk.value, cls.value, sep.value
+
+    @staticmethod
+    def _pack(texts):
+        import numpy as np
+
+        enc = [t.encode("utf-8", "replace") for t in texts]
+        offs = np.zeros(len(enc) + 1, dtype=np.int64)
+        if enc:
+            offs[1:] = np.cumsum([len(b) for b in enc])
+        return b"".join(enc), offs
+
+    def encode_packed(self, texts, max_len: int = 512, threads: int = 0):
+        """(tokens int32 [total], cu_seqlens int32 [n + 1]) -- the layout ``Encoder.encode_packed`` takes."""
+        import ctypes as C
+
+        import numpy as np
+
+        blob, offs = self._pack(texts)
+        n = len(offs) - 1
+        tokens = np.empty(max(1, n * max_len), dtype=np.int32)
+        cu = np.zeros(n + 1, dtype=np.int32)
+        self._N.check(self._lib.aur_tokenize(self._h, blob, offs.ctypes.data_as(C.c_void_p), n, int(max_len),
+                                             tokens.ctypes.data_as(C.c_void_p), tokens.size, cu.ctypes.data_as(C.c_void_p), int(threads)))
+        return tokens[: int(cu[-1])], cu
+
+    def encode_batch(self, texts, max_len: int = 512) -> List[List[int]]:
+        tok, cu = self.encode_packed(texts, max_len)
+        return [tok[cu[i]:cu[i + 1]].tolist() for i in range(len(cu) - 1)]
+
+    def encode(self, text: str, max_len: int = 512) -> List[int]:
+        return self.encode_batch([text], max_len)[0]
+
+    __call__ = encode
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.aur_tokenizer_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define AUR_ABI_VERSION 1
+#define AUR_ABI_VERSION 2
 
 typedef enum aur_status {
   AUR_OK = 0,
@@ -80,6 +80,9 @@ typedef struct aur_stats {
   int32_t last_launches; /* kernels launched by the last search                     */
   float   last_kernel_ms;/* device time of the dominant kernel of the last search   */
   float   last_total_ms; /* device time of the whole last search                    */
+  float   last_finalize_ms; /* from the end of the (first) similarity kernel to the end of the last exact
+                               re-rank kernel (for nq > 256 this spans the later query blocks too)         */
+  float   last_merge_ms; /* aur_search_exchange_dev: delivery wait + cross-shard merge; else ~0           */
 } aur_stats;
 
 int aur_abi_version(void);
@@ -111,6 +114,10 @@ int aur_add_dev(aur_index* ix, const void* rows_dev, const int64_t* ids_host,
  * compacts the tombstones away.  user_out / org_out may be NULL. */
 int aur_export(aur_index* ix, void* rows_out, int64_t* ids_out, int32_t* user_out,
                int32_t* org_out, uint8_t* live_out, int64_t n);
+
+/* Reads back rows [row0, row0 + n) of the published prefix (append order, tombstones included) with their ids:
+ * a partial aur_export, e.g. to snapshot only what was appended since the last snapshot. */
+int aur_read_rows(aur_index* ix, int64_t row0, int64_t n, void* rows_out, int64_t* ids_out);
 
 /* Reclaims the tombstones left by upserts and deletes (the reference's prediscovery job deletes and
  * re-inserts its chunks periodically, weaviate_client.py:374-394): live rows move down in append order,
@@ -256,6 +263,27 @@ int aur_encode_append(aur_encoder* enc, aur_index* ix, const int32_t* tokens,
                       const int32_t* cu_seqlens, int32_t n_seq, const int64_t* ids,
                       const int32_t* user_codes, const int32_t* org_codes);
 int aur_encoder_get_stats(aur_encoder* enc, aur_encoder_stats* out);
+
+/* ------------------------------------------------------------------ WordPiece tokenizer
+ * Text -> token ids on the host cores, multi-threaded.  In the reference this step is inside the t2v sidecar
+ * (raw text is posted to it, embedding_client.py:52-59); semantics = transformers.BertTokenizer (the `tokenizers`
+ * BertNormalizer + BertPreTokenizer + WordPiece): see csrc/tokenizer.cpp.  Texts travel as one UTF-8 buffer plus
+ * offsets [n_texts + 1]. */
+typedef struct aur_tokenizer aur_tokenizer;
+int aur_tokenizer_open(const char* vocab_path, int32_t lower_case, aur_tokenizer** out);       /* vocab.txt, one piece per line */
+int aur_tokenizer_open_mem(const char* vocab_utf8, int64_t nbytes, int32_t lower_case, aur_tokenizer** out);
+int aur_tokenizer_close(aur_tokenizer* t);
+int aur_tokenizer_info(aur_tokenizer* t, int32_t* vocab_size, int32_t* unk_id, int32_t* cls_id, int32_t* sep_id);
+/* Every text -> [CLS] pieces [SEP] truncated to max_len ids, packed: tokens_out (capacity tokens_cap; n_texts * max_len
+ * always suffices) and cu_seqlens_out [n_texts + 1].  n_threads 0 = all host cores. */
+int aur_tokenize(aur_tokenizer* t, const char* texts_utf8, const int64_t* offsets, int32_t n_texts, int32_t max_len,
+                 int32_t* tokens_out, int64_t tokens_cap, int32_t* cu_seqlens_out, int32_t n_threads);
+/* Text in, rows in the shard: tokenise, encoder forward, append -- insert_chunks (weaviate_client.py:136-212) without
+ * Python on the path.  Batches are cut to max_tokens_per_call / max_seqs_per_call (the encoder's workspace). */
+int aur_encode_text_append(aur_encoder* enc, aur_tokenizer* tok, aur_index* ix, const char* texts_utf8,
+                           const int64_t* offsets, int32_t n_texts, int32_t max_len, int32_t max_tokens_per_call,
+                           int32_t max_seqs_per_call, const int64_t* ids, const int32_t* user_codes,
+                           const int32_t* org_codes, int32_t n_threads);
 
 /* Bring-up / test hooks (not part of the drop-in surface). */
 /* out[M,N] = epi(A[M,K] . W[N,K]^T + bias) through the encoder's tcgen05 GEMM; host buffers,

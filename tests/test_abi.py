@@ -38,7 +38,7 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.aur_abi_version() == 1
+    assert lib.aur_abi_version() == N.ABI_VERSION == 2
     assert isinstance(lib.aur_last_error(), bytes)
 
 

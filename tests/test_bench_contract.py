@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _run(extra_env):
-    env = dict(os.environ, AUR_BENCH_SAMPLE="8000", **extra_env)
+    env = dict(os.environ, AUR_BENCH_ROWS="16000", **extra_env)      # (the real arm scans the full 1M rows per step)
     return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                           capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
 
@@ -23,7 +23,8 @@ def test_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "queries/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["metric"].startswith("RAG queries/sec")
-    assert d["config"]["rows"] == 1_000_000 and d["config"]["dim"] == 768 and d["config"]["k"] == 32
+    assert d["config"]["rows"] == 16_000 and d["config"]["dim"] == 768 and d["config"]["k"] == 32 and d["config"]["nq"] == 256
+    assert "no extrapolation" in d["cpu_baseline"]["sample"] and d["cpu_baseline"]["threads"] >= 1
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

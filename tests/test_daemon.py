@@ -15,7 +15,7 @@ def daemon(tmp_path):
     path = str(tmp_path / "kb.sock")
     srv = serve(path, background=True)
     yield path
-    srv.shutdown(); srv.server_close()
+    srv.shutdown(); srv.close_all(final_save=False); srv.server_close()
     R.configure(factory=lambda: (_ for _ in ()).throw(RuntimeError("backend down")))
 
 
@@ -76,3 +76,111 @@ def test_bootstrap_requires_its_variables(monkeypatch):
     with pytest.raises(ValueError):
         bootstrap._model_config("gpt-2")
     assert bootstrap._model_config("minilm-l6").hidden == 384
+
+
+def test_socket_is_private_and_facade_and_learn_over_the_wire(tmp_path):
+    import os
+    import stat
+
+    from aurora_b200 import incident_knowledge as K
+    from aurora_b200.filters import Filter, HybridFusion
+
+    R.configure(encoder=HashEmbedder(64), capacity=1024, index_factory=lambda dim, cap: OracleIndex(dim, cap))
+    K.configure(encoder=HashEmbedder(64), capacity=256, index_factory=lambda dim, cap: OracleIndex(dim, cap), org_resolver=lambda u: "acme")
+    path = str(tmp_path / "kb.sock")
+    srv = serve(path, background=True, learn_module=K)
+    try:
+        assert stat.S_IMODE(os.stat(path).st_mode) == 0o600            # any process that can open it reads every tenant
+        kb = Client(path)
+        kb.insert_chunks("u", "discovery:20260101:ab", "gke-topology", _chunks("checkout depends on payments and redis"), org_id="o")
+        kb.insert_chunks("u", "other", "notes.md", _chunks("checkout depends on payments and redis"), org_id="o")
+        # chat/background/rca_prompt_builder.py:276-317, unchanged, against the daemon client
+        _, collection = kb._get_weaviate_client()
+        f = Filter.by_property("org_id").equal("o") & Filter.by_property("document_id").like("discovery:*")
+        resp = collection.query.hybrid(query="checkout payments", limit=3, alpha=0.5, fusion_type=HybridFusion.RANKED,
+                                       filters=f, return_metadata=["score"])
+        assert [o.properties["source_filename"] for o in resp.objects] == ["gke-topology"] and resp.objects[0].metadata.score > 0
+        assert kb.store_good_rca("alice", "inc-1", "fb-1", "Payments API latency high", "payments", "grafana", "critical",
+                                 "pool exhausted", [{"content": "checked pool"}], [], org_id="acme") is True
+        hits = kb.search_similar_good_rcas("bob", "Payments API latency high", "payments", "grafana", limit=2, min_score=0.2)
+        assert hits and hits[0]["incident_id"] == "inc-1" and hits[0]["thoughts"] == [{"content": "checked pool"}]
+        assert kb.delete_incident_knowledge("alice", "inc-1") is True and kb.delete_user_knowledge("alice") == 0
+    finally:
+        srv.shutdown(); srv.close_all(final_save=False); srv.server_close()
+        R.configure(factory=lambda: (_ for _ in ()).throw(RuntimeError("backend down")))
+        K.configure(factory=lambda: (_ for _ in ()).throw(RuntimeError("backend down")), org_resolver=lambda u: None)
+    off = Client(str(tmp_path / "gone.sock"))
+    assert off.store_good_rca("a", "i", "f", "t", "s", "g", "c", "s", [], []) is False and off.search_similar_good_rcas("a", "t", "s", "g") == []
+    assert off.delete_incident_knowledge("a", "i") is False and off.delete_user_knowledge("a") == -1
+    with pytest.raises(Exception):
+        off._get_weaviate_client()
+
+
+def test_concurrent_searches_are_coalesced_into_encoder_batches(tmp_path):
+    """64 client threads, one query each at a time (the reference's call pattern): the daemon gathers them into a few
+    encoder batches instead of 64 x N single-sequence forwards, and every caller still gets exactly its own answer."""
+    emb = HashEmbedder(64)
+    R.configure(encoder=emb, capacity=4096, index_factory=lambda dim, cap: OracleIndex(dim, cap))
+    path = str(tmp_path / "kb.sock")
+    srv = serve(path, background=True, coalesce_us=20000)
+    try:
+        kb = Client(path)
+        for t in range(8):
+            kb.insert_chunks(f"user{t}", f"doc{t}", "f.md", _chunks(*[f"topic{t} item{i} runbook entry" for i in range(6)]))
+        calls_before = emb.calls
+        errs, n_threads, per_thread = [], 64, 5
+
+        def worker(i):
+            try:
+                c = Client(path)
+                for j in range(per_thread):
+                    t, it = i % 8, (i + j) % 6
+                    res = c.search_knowledge_base(f"user{t}", f"topic{t} item{it} runbook entry", limit=1, alpha=1.0)
+                    assert res[0]["document_id"] == f"doc{t}" and res[0]["chunk_index"] == it, (i, j, res)
+            except Exception as e:      # pragma: no cover
+                errs.append(e)
+
+        ts = [threading.Thread(target=worker, args=(i,)) for i in range(n_threads)]
+        [t.start() for t in ts]; [t.join() for t in ts]
+        assert not errs, errs[0]
+        encoder_calls = emb.calls - calls_before
+        h = kb.health()
+        assert h["coalesced_requests"] >= n_threads * per_thread
+        assert encoder_calls * 4 <= n_threads * per_thread, (encoder_calls, h)        # far fewer encoder batches than requests
+    finally:
+        srv.shutdown(); srv.close_all(final_save=False); srv.server_close()
+        R.configure(factory=lambda: (_ for _ in ()).throw(RuntimeError("backend down")))
+
+
+def test_snapshot_policy_saves_and_restores(tmp_path):
+    import os
+
+    emb = HashEmbedder(64)
+    R.configure(encoder=emb, capacity=1024, index_factory=lambda dim, cap: OracleIndex(dim, cap))
+    snap = str(tmp_path / "snap")
+    path = str(tmp_path / "kb.sock")
+    srv = serve(path, background=True, snapshot_dir=snap, save_every=3, save_seconds=3600)
+    try:
+        kb = Client(path)
+        kb.insert_chunks("u", "d", "f.md", _chunks("redis failover steps", "postgres vacuum", "kafka lag"))     # 3 mutations >= save_every
+        deadline = __import__("time").time() + 10
+        while not os.path.exists(os.path.join(snap, "meta.json")) and __import__("time").time() < deadline:
+            __import__("time").sleep(0.1)
+        assert os.path.exists(os.path.join(snap, "meta.json")) and kb.health()["unsaved_mutations"] == 0
+        kb.insert_chunks("u", "d2", "g.md", _chunks("one more"))
+        assert kb.health()["unsaved_mutations"] == 1
+        assert kb.save()["saved"] is True and kb.health()["unsaved_mutations"] == 0          # on demand
+        kb.delete_document_chunks("u", "d2")
+    finally:
+        srv.shutdown(); srv.close_all(final_save=True); srv.server_close()                       # the shutdown path saves too
+    b = R.KnowledgeBase.load(snap, emb, capacity=1024, index_loader=lambda p, cap: OracleIndex.load(p, cap))
+    assert b.count_where(lambda p: p["document_id"] == "d") == 3 and b.count_where(lambda p: p["document_id"] == "d2") == 0
+    assert [n for n in os.listdir(snap) if n.startswith("shard.")] == [json_meta(snap)["shard"]]     # one generation on disk
+    R.configure(factory=lambda: (_ for _ in ()).throw(RuntimeError("backend down")))
+
+
+def json_meta(snap):
+    import json
+    import os
+
+    return json.load(open(os.path.join(snap, "meta.json")))

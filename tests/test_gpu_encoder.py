@@ -259,6 +259,56 @@ def test_retriever_with_cuda_encoder_end_to_end():
         enc.close()
 
 
+def test_reference_chunker_output_through_tokenizer_encoder_and_shard():
+    """SURVEY.md 8 a9 -> a4: the chunks the REAL reference chunker produced (tests/golden/chunker_ref.json, generated by
+    oracle/gen_golden_chunks.py from document_processor.py) go through insert_chunks -> C++ WordPiece -> CUDA encoder ->
+    shard, one aur_encode_text_append call per document; every chunk is then found again by its own text.  The
+    4 196-character chunk (document_processor.py:266-267) exceeds the 512-token position table: it is embedded as the
+    normalised mean of its token windows instead of being cut off."""
+    from aurora_b200 import retriever as R
+    from aurora_b200.encoder import TextEncoder
+    from aurora_b200.wordpiece import NativeTokenizer, basic_tokenize
+
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "chunker_ref.json"), encoding="utf-8"))
+    docs = [d for d in gold["documents"] if d["chunks"]]
+    words = sorted({w for d in docs for c in d["chunks"] for w in basic_tokenize(c["heading_context"] + " " + c["content"])})
+    pieces = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"] + [w for w in words if len(w) <= 100]
+    cfg_o = B.BertConfig(hidden=128, layers=2, heads=2, inter=256, vocab=len(pieces), max_pos=512, pool="cls")
+    enc = Encoder(_mirror(cfg_o), max_tokens=8192, max_seqs=64)
+    enc.load_weights(B.init_weights(cfg_o, seed=11, bf16=True))
+    tok = NativeTokenizer(pieces)
+    te = TextEncoder(enc, tok)
+    R.configure(encoder=te, capacity=1024, device=0)
+    try:
+        total = 0
+        for d in docs:
+            n = R.insert_chunks("user-1", f"doc-{d['name']}", d["name"], d["chunks"], org_id="org-1")
+            assert n == len(d["chunks"])
+            assert R.get_document_chunk_count("user-1", f"doc-{d['name']}") == n
+            total += n
+        big = next(c for d in docs for c in d["chunks"] if len(c["content"]) > 4000)
+        assert len(te._windows(big["content"])) >= 2                                   # really longer than the position table
+        for d in docs:
+            for c in d["chunks"]:
+                text = (c["heading_context"] + "\n" if c["heading_context"] else "") + c["content"]
+                if len(set(basic_tokenize(text))) < 3:
+                    continue                                                        # ('xxxx...' chunks: all [UNK], identical vectors)
+                hits = R.search_knowledge_base("user-1", text, limit=1, alpha=1.0)
+                assert hits and hits[0]["document_id"] == f"doc-{d['name']}" and hits[0]["chunk_index"] == c["chunk_index"], (d["name"], c["chunk_index"])
+                assert hits[0]["score"] > 0.999
+        # the over-long chunk's stored vector is the normalised mean of its windows' vectors
+        wins = te._windows(big["content"])
+        from aurora_b200.encoder import pack_sequences
+        wv = enc.encode_packed(*pack_sequences(wins))
+        mean = wv.mean(axis=0); mean /= np.linalg.norm(mean)
+        got = te.encode([big["content"]])[0]
+        assert float(np.dot(got, mean)) > 0.9999
+    finally:
+        R.configure(encoder=None)
+        tok.close()
+        enc.close()
+
+
 def test_bootstrap_from_environment_end_to_end(tmp_path, monkeypatch):
     """aurora_b200.bootstrap.configure_from_env: safetensors checkpoint (HF names) + vocab.txt -> CUDA encoder
     + shard behind the reference's module API, then snapshot -> restore.  all-MiniLM-L6-v2 dimensions

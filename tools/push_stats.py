@@ -13,7 +13,7 @@ with Index(d, n) as ix:
     for lo in range(0, n, 50_000):
         m = min(50_000, n - lo)
         ix.add(np.roll(block[:m], lo // 50_000, axis=1), np.arange(lo, lo + m, dtype=np.int64))
-    N.check(ix._lib.aur_set_option(ix._h, b"dbg_flags", 64))
+    N.check(ix._lib.aur_set_option(ix._h, b"dbg_flags", 64 | int(os.environ.get("AUR_DBG_FLAGS", "0"))))
     g = 1
     if os.environ.get("AUR_EPI_GROUPS"):
         N.check(ix._lib.aur_set_option(ix._h, b"epi_groups", int(os.environ["AUR_EPI_GROUPS"])))
@@ -36,6 +36,9 @@ for grp in range(g):
 mm = out[0::2, 0, 32:35]
 print(f"MMA warp cycles: total {mm[:,2].mean():.0f} wait_tmem_empty {mm[:,0].mean():.0f} ({100*mm[:,0].mean()/mm[:,2].mean():.0f}%) "
       f"wait_smem_full {mm[:,1].mean():.0f} ({100*mm[:,1].mean()/mm[:,2].mean():.0f}%)")
+pp = out[:, 0, 36:39]
+print(f"TMA producer cycles: total {pp[:,1].mean():.0f} wait_smem_empty {pp[:,0].mean():.0f} ({100*pp[:,0].mean()/max(pp[:,1].mean(),1):.0f}%); "
+      f"streaming phase {pp[:,2].mean()/1e3:.1f} us -> SM clock {pp[:,1].mean()/max(pp[:,2].mean(),1)*1e3:.0f} MHz")
 ts = out[:, :, 9]; ns = out[:, :, 1]
 flat = np.argsort(-ts.ravel())[:12]
 for f in flat:
