@@ -122,6 +122,7 @@ struct SearchCtx {
   DevBuf<uint64_t> cand_a, cand_b;
   DevBuf<uint64_t> pub;          // tcgen05 kernel's cross-CTA threshold exchange
   DevBuf<uint32_t> cand_count;   // compacted candidates per query (self-resetting)
+  DevBuf<uint32_t> d_epoch;      // the tcgen05 kernel's launch counter, device resident (CUDA-graph replays advance it)
   DevBuf<float> score_chunk;
   DevBuf<float> masked_inv;      // inverse norms with the invisible rows turned into NaN (tenant scope / id subset)
   DevBuf<int32_t> allow_rows;    // subset search: rows that stay visible
@@ -130,7 +131,7 @@ struct SearchCtx {
   DevBuf<float> stage_scores;
   DevBuf<int64_t> stage_ids;
   void release() {
-    cand_a.release(); cand_b.release(); pub.release(); cand_count.release(); score_chunk.release(); masked_inv.release();
+    cand_a.release(); cand_b.release(); pub.release(); cand_count.release(); d_epoch.release(); score_chunk.release(); masked_inv.release();
     allow_rows.release(); stage_q.release(); stage_quser.release(); stage_qorg.release(); stage_scores.release();
     stage_ids.release();
     if (ev_begin) cudaEventDestroy(ev_begin);
@@ -242,8 +243,17 @@ int run_tc_block(aur_index* ix, SearchCtx* c, int cta_group, const void* q_dev, 
     // TMA stages do not fit next to the lists (large k at dim > 768) it runs as a pair with a padding block
     if (tc_pick_stages(1, 1, ksel, ix->dim, ix->smem_optin) >= 2) cta_group = 1; else n_qblocks = 2;
   }
-  int grid = ix->sm_count & ~1;
-  const int n_tsets = (cta_group == 2) ? grid / 2 : grid / n_qblocks;
+  const int pairs = ix->sm_count / 2;
+  int n_super = 1;   // query super-blocks of 256 (CTA pairs that walk the same tiles side by side, sharing them through L2)
+  if (cta_group == 2) {
+    n_super = (nqb + 2 * kTcQRows - 1) / (2 * kTcQRows);
+    // the threshold exchange needs ceil(ksel / tile sets) <= 4 rows vouched for per CTA
+    while (n_super > 1 && (ksel + pairs / n_super - 1) / (pairs / n_super) > 4) --n_super;
+    if (nqb > n_super * 2 * kTcQRows) return fail(AUR_ERR_INVALID, "internal: query block larger than the launch geometry");
+    n_qblocks = 2 * n_super;
+  }
+  int grid = (cta_group == 2) ? (pairs / n_super) * n_super * 2 : (ix->sm_count & ~1);
+  const int n_tsets = (cta_group == 2) ? pairs / n_super : grid / n_qblocks;
   // epilogue groups: 1 by default; 2 (alternating tiles) stays selectable for experiments
   int epi_groups = ix->opt_epi_groups;
   if (epi_groups == 0) epi_groups = 1;   // measured: one group + a deeper TMA ring (11 stages) beats two groups + 8
@@ -258,11 +268,16 @@ int run_tc_block(aur_index* ix, SearchCtx* c, int cta_group, const void* q_dev, 
     CU_TRY(c->pub.reserve(npub));
     CU_TRY(cudaMemsetAsync(c->pub.p, 0, npub * 8, s));  // epoch 0 is never used by a launch
   }
-  if (c->cand_count.n < 2 * kTcQRows) {
-    CU_TRY(c->cand_count.reserve(2 * kTcQRows));
-    CU_TRY(cudaMemsetAsync(c->cand_count.p, 0, 2 * kTcQRows * 4, s));
+  if (c->cand_count.n < 8 * kTcQRows) {
+    CU_TRY(c->cand_count.reserve(8 * kTcQRows));
+    CU_TRY(cudaMemsetAsync(c->cand_count.p, 0, 8 * kTcQRows * 4, s));
   }
-  if (++c->epoch == 0) c->epoch = 1;
+  if (c->d_epoch.n == 0) {
+    static const uint32_t one = 1;
+    CU_TRY(c->d_epoch.reserve(1));
+    CU_TRY(cudaMemcpyAsync(c->d_epoch.p, &one, 4, cudaMemcpyHostToDevice, s));
+  }
+  ++c->epoch;
   TcParams p;
   p.q = static_cast<const __nv_bfloat16*>(q_dev);
   p.inv_norm = inv_norm ? inv_norm : ix->d_inv_norm;
@@ -270,7 +285,10 @@ int run_tc_block(aur_index* ix, SearchCtx* c, int cta_group, const void* q_dev, 
   p.cand_count = c->cand_count.p;
   p.dbg_scores = dbg;
   p.pub = c->pub.p;
-  p.epoch = c->epoch;
+  // searches: device-resident counter, advanced by the finalize kernel that follows; the bring-up entry point (no
+  // finalize behind it) tags its entries from a disjoint range on the host
+  p.epoch = 0x80000000u | c->epoch;
+  p.epoch_ptr = dbg ? nullptr : c->d_epoch.p;
   p.n_rows = n_rows;
   p.nq = nqb; p.dim = ix->dim; p.ksel = ksel; p.n_lists = n_lists; p.n_qblocks = n_qblocks;
   p.num_stages = stages;
@@ -326,7 +344,16 @@ int search_enqueue(aur_index* ix, SearchCtx* c, const void* q_dev, int nq, int k
     inv = c->masked_inv.p;
   }
 
-  const int qstep = (kernel == AUR_KERNEL_SIMT) ? 1024 : 2 * kTcQRows;
+  // queries per launch: the generic kernel takes 1024; the tcgen05 kernel 256 per CTA pair and up to four pairs side by
+  // side on the same corpus tiles (fewer when k + slack is too large for the threshold exchange of that geometry)
+  int qstep = 1024;
+  if (kernel == AUR_KERNEL_TC1) qstep = 2 * kTcQRows;
+  else if (kernel == AUR_KERNEL_TC2) {
+    const int pairs = ix->sm_count / 2;
+    int n_super = 4;
+    while (n_super > 1 && (ksel + pairs / n_super - 1) / (pairs / n_super) > 4) --n_super;
+    qstep = n_super * 2 * kTcQRows;
+  }
   for (int q0 = 0; q0 < nq; q0 += qstep) {
     const int nqb = (nq - q0 < qstep) ? nq - q0 : qstep;
     const uint8_t* qb = static_cast<const uint8_t*>(q_dev) + static_cast<size_t>(q0) * ix->dim * ix->elt;
@@ -381,12 +408,13 @@ int search_enqueue(aur_index* ix, SearchCtx* c, const void* q_dev, int nq, int k
     FinalizeArgs fa{};
     fa.cand = cur; fa.n_lists = n_lists; fa.ksel = ksel;
     fa.counts = compact ? c->cand_count.p : nullptr;
+    fa.epoch_bump = compact ? c->d_epoch.p : nullptr;
     fa.q = qb; fa.rows = ix->d_rows; fa.dtype = ix->dtype; fa.dim = ix->dim; fa.nq = nqb; fa.k = k;
     fa.ids = ix->d_ids;
     fa.out_scores = scores ? scores + static_cast<size_t>(q0) * k : nullptr;
     fa.out_ids = ids ? ids + static_cast<size_t>(q0) * k : nullptr;
     fa.out_scores64 = scores64 ? scores64 + static_cast<size_t>(q0) * k : nullptr;
-    if (ex) { fa.ex = *ex; fa.ex.q0 = q0; }
+    if (ex) { fa.ex = *ex; fa.ex.q0 = q0; fa.ex.signal = (q0 + qstep >= nq) ? ex->signal : 0; }   // only the last launch signals
     CU_TRY(launch_finalize(fa, s));
     c->last_launches += 1;
   }
@@ -857,8 +885,8 @@ int aur_exchange_create(int32_t device, int32_t rank, int32_t world, int32_t nq_
   if (e == cudaSuccess) e = cudaMemset(ex->local, 0, ex->bytes);
   if (e == cudaSuccess) e = cudaMalloc(&ex->d_seq, 8);
   if (e == cudaSuccess) e = cudaMemset(ex->d_seq, 0, 8);
-  if (e == cudaSuccess) e = cudaMalloc(&ex->d_done, 8);
-  if (e == cudaSuccess) e = cudaMemset(ex->d_done, 0, 8);
+  if (e == cudaSuccess) e = cudaMalloc(&ex->d_done, 16);      // [0] merge block counter, [1] status, [2] finalize block counter
+  if (e == cudaSuccess) e = cudaMemset(ex->d_done, 0, 16);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   cudaIpcMemHandle_t h;
   if (e == cudaSuccess && world > 1) e = cudaIpcGetMemHandle(&h, ex->local);
@@ -931,6 +959,10 @@ int aur_search_exchange_dev(aur_index* ix, aur_exchange* ex, const void* queries
   eo.seq = ex->d_seq;
   eo.parity_stride = ex->parity_stride;
   eo.plane_stride = ex->plane;
+  for (int r = 0; r < ex->world; ++r) eo.flag[r] = ex->peer[r] + ex->flags_off + ex->rank;
+  eo.done = ex->d_done + 2;
+  eo.flag_parity_stride = ex->world;
+  eo.signal = 1;
   Scope sc;
   rc = search_enqueue(ix, c, queries_dev, nq, k, sc, ix->rows_pub.load(std::memory_order_acquire), nullptr, nullptr, nullptr, s, &eo);
   if (rc != AUR_OK) return rc;
@@ -939,6 +971,7 @@ int aur_search_exchange_dev(aur_index* ix, aur_exchange* ex, const void* queries
   for (int r = 0; r < ex->world; ++r) p.peer_flags[r] = ex->peer[r] + ex->flags_off;
   p.seq = ex->d_seq; p.done = ex->d_done; p.status = ex->d_done + 1;
   p.world = ex->world; p.rank = ex->rank; p.nq = nq; p.k = k;
+  p.signal = 0;     // the finalize kernel's last block raised the flags already
   p.parity_stride = ex->parity_stride; p.slot_stride = ex->slot_stride; p.plane_stride = ex->plane;
   p.out_scores = scores_dev; p.out_ids = ids_dev;
   CU_TRY(launch_exchange_merge(p, s));
@@ -1020,7 +1053,7 @@ int aur_debug_tc_scores(aur_index* ix, const void* queries_dev, int32_t nq, int3
   rc = run_tc_block(ix, c, cta_group, queries_dev, nq, 32 + kSlack, ix->rows_pub.load(std::memory_order_acquire), out_dev,
                     &n_lists, s);
   if (rc != AUR_OK) return rc;
-  CU_TRY(cudaMemsetAsync(c->cand_count.p, 0, 2 * kTcQRows * 4, s));  // no finalize ran to reset them
+  CU_TRY(cudaMemsetAsync(c->cand_count.p, 0, 8 * kTcQRows * 4, s));  // no finalize ran to reset them
   if (n_ctas_out) *n_ctas_out = ix->sm_count & ~1;
   return AUR_OK;
 }

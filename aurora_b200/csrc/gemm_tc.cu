@@ -186,14 +186,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int tile = group; tile < n_tiles_total; tile += n_groups, ++it) {
       const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
       const int acc = it & 1;
-      mbar_wait(&acc_full[acc], (it >> 1) & 1);
-      tc_fence_after();
       const int row0 = (m_blk * G + static_cast<int>(rank)) * kBM + quarter * 32;
       const int col0 = n_blk * BN + half * kColsPerWarp;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * kColsPerWarp;
       const __nv_bfloat16* rrow = EPI == kEpiBiasResid ? p.resid + static_cast<size_t>(row0 + lane) * p.ldr + col0 : nullptr;
-#pragma unroll 1
-      for (int c = 0; c < kColsPerWarp; c += 64, slab ^= 1) {
+      // Residual: every lane reads 64 bytes of ITS row per 32-column unit -- 32 different lines per load instruction,
+      // ~1 us from L2.  The loads do not depend on the accumulator, so the first two units are requested BEFORE the
+      // wait for the MMAs of this tile and each later unit two units ahead of its use; with K = 768 (out-proj) a tile's
+      // MMAs last only ~6k cycles and the exposed latency used to make this epilogue the slower side of the pipeline.
+      constexpr int kUnits = kColsPerWarp / 32;
+      uint4 res_q[2][4];
+      auto load_res = [&](int u, uint4 (&r)[4]) {
+        if constexpr (EPI == kEpiBiasResid) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) r[j] = (u < kUnits) ? __ldg(reinterpret_cast<const uint4*>(rrow + 32 * u) + j) : make_uint4(0, 0, 0, 0);
+        }
+      };
+      load_res(0, res_q[0]);
+      load_res(1, res_q[1]);
+      mbar_wait(&acc_full[acc], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int cu = 0; cu < kColsPerWarp / 64; ++cu, slab ^= 1) {
+        const int c = cu * 64;
         uint8_t* buf = my_stage + slab * 4096;
         // the TMA store that last read this slab (two slabs ago) must have drained it
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -205,7 +220,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           uint4 res[4];
           if constexpr (EPI == kEpiBiasResid) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) res[j] = __ldg(reinterpret_cast<const uint4*>(rrow + c + 32 * hh) + j);
+            for (int j = 0; j < 4; ++j) res[j] = res_q[hh][j];
+            load_res(2 * cu + hh + 2, res_q[hh]);          // two units ahead
           }
           tmem_wait_ld();
           uint32_t o[16];

@@ -61,6 +61,7 @@ struct TcParams {
                             // then [n_qblocks, 128] the served thresholds
   int64_t n_rows;
   uint32_t epoch;           // launch counter: pub entries of older launches are ignored
+  const uint32_t* epoch_ptr;// when set, the counter lives in device memory (bumped by the finalize kernel)
   int nq, dim, ksel, n_lists, n_qblocks, num_stages, n_tiles;
   int dbg_flags;            // bring-up only (timing decomposition; results are wrong with 1..32): 1 = epilogue neither
                             // reads nor examines the accumulator, 2 = no MMAs issued, 4 = accumulator read but not
@@ -103,6 +104,7 @@ struct FinalizeArgs {
   const uint64_t* cand; int n_lists; int ksel;
   uint32_t* counts;  // nullable: per-query number of valid keys at the front of its cand row
                      // (reset to 0 by the kernel); null = all n_lists * ksel slots are keys
+  uint32_t* epoch_bump;  // nullable: the tcgen05 kernel's device-resident launch counter, advanced here (never 0)
   const void* q; const void* rows; int dtype; int dim; int nq; int k;
   const int64_t* ids;
   float* out_scores; int64_t* out_ids; double* out_scores64;   // (out_scores / out_ids nullable in exchange mode)
@@ -116,6 +118,12 @@ struct FinalizeArgs {
     size_t parity_stride;       // 8-byte words between the two parities of a buffer
     size_t plane_stride;        // words between the score plane and the id plane of a slot
     int q0;                     // first query of this launch inside the batch
+    // delivery signal, raised by the last block of the LAST finalize launch of a search (signal != 0): flag[r] is this
+    // rank's entry (parity 0) in rank r's flag array; done counts finished blocks (self-resetting)
+    uint64_t* flag[8];
+    uint32_t* done;
+    int flag_parity_stride;     // words between the two parities of a flag array (= world)
+    int signal;
   } ex;
 };
 // Cross-shard merge fed by the peer stores above: signal every peer, wait for all of them, keep the best k.
@@ -127,6 +135,7 @@ struct ExchangeParams {
   uint32_t* done;               // block counter (self-resetting)
   uint32_t* status;             // != 0: a peer did not deliver in time
   int world, rank, nq, k;
+  int signal;                   // != 0: this kernel raises the delivery flags itself (else the finalize kernel did)
   size_t parity_stride, slot_stride, plane_stride;
   float* out_scores; int64_t* out_ids;
 };

@@ -21,6 +21,13 @@ __device__ __forceinline__ double warp_sum_lane0(double v) {
   return __shfl_sync(0xffffffffu, v, 0);
 }
 
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+  uint64_t v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 // --------------------------------------------------------------------------------------
 // Inverse L2 norm per appended row (one warp per row).  Weaviate normalises vectors at
 // import for the cosine metric; we keep the raw rows and this scale beside them.
@@ -102,10 +109,49 @@ simt_scores_kernel(const T* __restrict__ q, const T* __restrict__ rows, int dim,
 }
 
 // --------------------------------------------------------------------------------------
-// Block-wide bitonic sort, descending, n a power of two, keys in shared memory.
+// Block-wide bitonic sort, descending, n a power of two >= 64, keys in shared memory.
+// A step (k, j) compares elements i and i ^ j.  All steps with j <= 32 stay inside an aligned block of 64 keys: a warp
+// takes such a block into registers (two keys per lane: i and i + 32), runs those steps with shuffles and writes the
+// block back -- no block barrier in between.  Only the steps with j >= 64 go through shared memory with a barrier
+// each.  A 512-key sort needs 10 barriers instead of 45; the exact-re-rank kernel is a latency chain and most of its
+// time used to be spent waiting at them.
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
+  const uint32_t lo = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(v), m);
+  const uint32_t hi = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(v >> 32), m);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+// Steps j = j_hi, j_hi / 2, ..., 1 of level k on every 64-key block (j_hi <= 32); with all_levels, levels 2 .. 64 in full.
+__device__ void bitonic_local64(uint64_t* s, int n, int k, bool all_levels) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int base = warp * 64; base < n; base += nwarps * 64) {
+    const int i0 = base + lane, i1 = i0 + 32;
+    uint64_t e0 = s[i0], e1 = s[i1];
+    auto step = [&](int kk, int j) {
+      if (j == 32) {
+        const bool desc = (i0 & kk) == 0;
+        if ((e0 < e1) == desc) { const uint64_t t = e0; e0 = e1; e1 = t; }
+      } else {
+        const uint64_t o0 = shfl_xor_u64(e0, j), o1 = shfl_xor_u64(e1, j);
+        const bool lower = (lane & j) == 0;
+        const bool want_max0 = ((i0 & kk) == 0) == lower, want_max1 = ((i1 & kk) == 0) == lower;
+        e0 = want_max0 ? (e0 > o0 ? e0 : o0) : (e0 < o0 ? e0 : o0);
+        e1 = want_max1 ? (e1 > o1 ? e1 : o1) : (e1 < o1 ? e1 : o1);
+      }
+    };
+    if (all_levels) {
+      for (int kk = 2; kk <= 64; kk <<= 1)
+        for (int j = kk >> 1; j > 0; j >>= 1) step(kk, j);
+    } else {
+      for (int j = 32; j > 0; j >>= 1) step(k, j);
+    }
+    s[i0] = e0; s[i1] = e1;
+  }
+  __syncthreads();
+}
 __device__ void bitonic_desc(uint64_t* s, int n) {
-  for (int k = 2; k <= n; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
+  bitonic_local64(s, n, 0, true);
+  for (int k = 128; k <= n; k <<= 1) {
+    for (int j = k >> 1; j >= 64; j >>= 1) {
       for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int l = i ^ j;
         if (l > i) {
@@ -116,6 +162,7 @@ __device__ void bitonic_desc(uint64_t* s, int n) {
       }
       __syncthreads();
     }
+    bitonic_local64(s, n, k, false);
   }
 }
 
@@ -151,7 +198,7 @@ reduce_lists_kernel(const uint64_t* __restrict__ in, int n_lists, int ksel, int 
   const int g = blockIdx.x, qi = blockIdx.y;
   const int l0 = g * group, l1 = min(n_lists, l0 + group);
   const int n = (l1 - l0) * ksel;
-  int P = 1; while (P < n) P <<= 1;
+  int P = 64; while (P < n) P <<= 1;
   const uint64_t* src = in + (static_cast<size_t>(qi) * n_lists + l0) * ksel;
   for (int i = threadIdx.x; i < P; i += blockDim.x) skeys[i] = i < n ? src[i] : 0ull;
   __syncthreads();
@@ -187,10 +234,22 @@ finalize_kernel(FinalizeArgs a) {
   }
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");     // the candidate lists come from the previous kernel
+  if (a.epoch_bump && blockIdx.x == 0 && threadIdx.x == 0) {   // that kernel is complete: next launch, next epoch
+    uint32_t e = *a.epoch_bump + 1;
+    *a.epoch_bump = e ? e : 1u;
+  }
 
   const int cap = a.n_lists * a.ksel;                       // row stride of cand
-  const int n = a.counts ? min(static_cast<int>(a.counts[qi]), cap) : cap;
   const uint64_t* src = a.cand + static_cast<size_t>(qi) * cap;
+  // the first keys of the row are requested together with the count that says how many of them are valid: one global
+  // round trip instead of two (slots past the count hold stale keys of earlier searches and are masked below)
+  uint64_t spec[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int i = threadIdx.x + u * 256;
+    spec[u] = (a.counts && i < cap) ? src[i] : 0ull;
+  }
+  const int n = a.counts ? min(static_cast<int>(a.counts[qi]), cap) : cap;
   // Sort in rounds of at most sort_cap keys; the best ksel of earlier rounds ride along
   // at the front.  (One round unless a compacted row overflows the sort buffer.)
   int P = 1;
@@ -199,8 +258,14 @@ finalize_kernel(FinalizeArgs a) {
     do {
       const int take = min(n - done, a.sort_cap - carried);
       const int m = carried + take;
-      P = 1; while (P < m) P <<= 1;
-      for (int i = carried + threadIdx.x; i < P; i += blockDim.x) skeys[i] = (i < m) ? src[done + i - carried] : 0ull;
+      P = 64; while (P < m) P <<= 1;
+      if (a.counts && done == 0 && blockDim.x == 256) {      // first round: the speculative loads cover slots 0 .. 511
+        if (static_cast<int>(threadIdx.x) < P) skeys[threadIdx.x] = (static_cast<int>(threadIdx.x) < m) ? spec[0] : 0ull;
+        if (static_cast<int>(threadIdx.x) + 256 < P) skeys[threadIdx.x + 256] = (static_cast<int>(threadIdx.x) + 256 < m) ? spec[1] : 0ull;
+        for (int i = threadIdx.x + 512; i < P; i += blockDim.x) skeys[i] = (i < m) ? src[i] : 0ull;
+      } else {
+        for (int i = carried + threadIdx.x; i < P; i += blockDim.x) skeys[i] = (i < m) ? src[done + i - carried] : 0ull;
+      }
       __syncthreads();
       bitonic_desc(skeys, P);
       done += take;
@@ -318,6 +383,19 @@ finalize_kernel(FinalizeArgs a) {
   if (threadIdx.x == 0) { int nv = 0; for (int u = 0; u < ncand; ++u) nv += ex_id[u] >= 0; s_nvalid = nv; }
   __syncthreads();
   for (int t = s_nvalid + threadIdx.x; t < a.k; t += blockDim.x) emit(t, -INFINITY, -1);
+  if (a.ex.n_peers > 0 && a.ex.signal) {
+    // Delivery signal of the fused exchange: once EVERY block of this (last) finalize launch has pushed its rows to
+    // the peers, tell each peer "rank r delivered exchange #seq".  Every thread fences its own peer stores at system
+    // scope, the block barrier orders them before thread 0's counter bump, and the last block releases the flags.
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(a.ex.done, 1u) == gridDim.x - 1) {
+      *a.ex.done = 0;
+      const uint64_t seq = *a.ex.seq + 1;
+      __threadfence_system();
+      for (int r = 0; r < a.ex.n_peers; ++r) st_release_sys(a.ex.flag[r] + (seq & 1ull) * a.ex.flag_parity_stride, seq);
+    }
+  }
 }
 
 // Cross-shard merge of exact (fp64 score, id) lists: [n_shards, nq, k] -> [nq, k].
@@ -370,12 +448,6 @@ merge_topk_kernel(const double* __restrict__ in_s, const int64_t* __restrict__ i
 //   4. the last block to finish bumps the sequence word, so a replayed CUDA graph advances by itself.
 // Two parities: rank A can only write exchange s+2 after its own merge s+1, which waited for B's delivery s+1,
 // which B issued after finishing its merge s -- so a slot is never overwritten while someone still reads it.
-__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
-  uint64_t v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
-}
-__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 
 __global__ void __launch_bounds__(256)
 exchange_merge_kernel(ExchangeParams p) {
@@ -386,7 +458,7 @@ exchange_merge_kernel(ExchangeParams p) {
   const uint64_t seq = *p.seq + 1;
   const size_t par = (seq & 1ull) * p.parity_stride;
   const int qi = blockIdx.x, n = p.world * p.k;
-  if (blockIdx.x == 0 && threadIdx.x < p.world) {
+  if (p.signal && blockIdx.x == 0 && threadIdx.x < p.world) {
     __threadfence_system();
     st_release_sys(p.peer_flags[threadIdx.x] + (seq & 1ull) * p.world + p.rank, seq);
   }
@@ -501,7 +573,7 @@ cudaError_t launch_simt_select(const float* scores, int nq, int64_t row0, int64_
 cudaError_t launch_reduce_lists(const uint64_t* in, int nq, int n_lists, int ksel, int group, uint64_t* out,
                                 cudaStream_t s) {
   const int n_groups = (n_lists + group - 1) / group;
-  int P = 1; while (P < group * ksel) P <<= 1;
+  int P = 64; while (P < group * ksel) P <<= 1;
   dim3 grid(static_cast<unsigned>(n_groups), static_cast<unsigned>(nq));
   reduce_lists_kernel<<<grid, 512, static_cast<size_t>(P) * 8, s>>>(in, n_lists, ksel, group, out, n_groups);
   return cudaGetLastError();
@@ -509,7 +581,7 @@ cudaError_t launch_reduce_lists(const uint64_t* in, int nq, int n_lists, int kse
 
 cudaError_t launch_finalize(const FinalizeArgs& a_in, cudaStream_t s) {
   FinalizeArgs a = a_in;
-  int P = 1; while (P < a.n_lists * a.ksel) P <<= 1;
+  int P = 64; while (P < a.n_lists * a.ksel) P <<= 1;
   if (P > kSortCap) {
     if (!a.counts) return cudaErrorInvalidValue;   // dense rows must be folded first
     P = kSortCap;

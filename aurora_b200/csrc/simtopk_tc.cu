@@ -97,7 +97,7 @@ struct TopkState {
   uint64_t min_key;   // smallest key, valid when the list holds exactly ksel entries (nfill == ksel)
   float tau_local;    // its score, else -inf
   float tau;          // admission filter = max(tau_local, certified global threshold)
-  float top1, top2;   // best two scores this thread has admitted (published for the exchange)
+  float top[4];       // best four chunk maxima seen so far (distinct rows), descending: top[xm - 1] is published
   int minpos, nfill;
 };
 
@@ -133,13 +133,8 @@ __device__ __noinline__ TopkState compact_list(TopkState st, uint32_t list_a, in
   return st;
 }
 
-// Admit one score into a query's list.  kTrackTop: also maintain the best two admitted scores (off when
-// the caller tracks the tile maxima itself).
-template <bool kTrackTop = true>
+// Admit one score into a query's list.
 __device__ __forceinline__ TopkState push_one(TopkState st, float s, int row, uint32_t list_a, int ksel, int lcap) {
-  if constexpr (kTrackTop) {
-    if (s > st.top1) { st.top2 = st.top1; st.top1 = s; } else if (s > st.top2) st.top2 = s;
-  }
   const uint64_t key = make_key(s, row);
   if (st.nfill == lcap) st = compact_list(st, list_a, ksel);
   if (st.nfill < lcap) {
@@ -166,6 +161,21 @@ __device__ __noinline__ TopkState push_group4(TopkState st, float s0, float s1, 
   return st;
 }
 
+// Running best four of the per-16-row chunk maxima.  Every chunk maximum belongs to a different corpus row, so
+// top[m - 1] >= v certifies "this CTA has m rows scoring at least v" -- what the threshold exchange needs when fewer
+// than k + slack CTAs scan the corpus (m = ceil((k + slack) / CTAs), up to 4).  Branch-free insertion network.
+__device__ __forceinline__ void top4_insert(float (&t)[4], float v) {   // v is never NaN (fmaxf drops NaN upstream)
+  float a = v;
+  const float n0 = fmaxf(t[0], a); a = fminf(t[0], a);
+  const float n1 = fmaxf(t[1], a); a = fminf(t[1], a);
+  const float n2 = fmaxf(t[2], a); a = fminf(t[2], a);
+  t[3] = fmaxf(t[3], a); t[0] = n0; t[1] = n1; t[2] = n2;
+}
+
+__device__ __forceinline__ float top4_get(const float (&t)[4], int m) {   // t[m - 1] without dynamic register indexing
+  return m == 1 ? t[0] : (m == 2 ? t[1] : (m == 3 ? t[2] : t[3]));
+}
+
 // Deferred slow path.  The hot loop only parks a group of four adjacent scores whose max reached the
 // threshold (two predicated shared-memory stores); this routine runs when a thread's FIFO is nearly
 // full and once at the end, re-tests the parked scores against the threshold as it stands NOW (usually
@@ -180,10 +190,10 @@ __device__ __noinline__ TopkState drain_fifo(TopkState st, uint32_t fifo_a, uint
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(row) : "r"(ftag_a + rec * (kTcQRows * 4u)));
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(s0), "=f"(s1), "=f"(s2), "=f"(s3)
                  : "r"(fifo_a + rec * (kTcQRows * 16u)));
-    if (s0 >= st.tau) st = push_one<false>(st, s0, row + 0, list_a, ksel, ksel);   // `>=` also rejects NaN
-    if (s1 >= st.tau) st = push_one<false>(st, s1, row + 1, list_a, ksel, ksel);
-    if (s2 >= st.tau) st = push_one<false>(st, s2, row + 2, list_a, ksel, ksel);
-    if (s3 >= st.tau) st = push_one<false>(st, s3, row + 3, list_a, ksel, ksel);
+    if (s0 >= st.tau) st = push_one(st, s0, row + 0, list_a, ksel, ksel);   // `>=` also rejects NaN
+    if (s1 >= st.tau) st = push_one(st, s1, row + 1, list_a, ksel, ksel);
+    if (s2 >= st.tau) st = push_one(st, s2, row + 2, list_a, ksel, ksel);
+    if (s3 >= st.tau) st = push_one(st, s3, row + 3, list_a, ksel, ksel);
   }
   return st;
 }
@@ -266,13 +276,20 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = (kCtaGroup == 2) ? cluster_ctarank() : 0u;
+  // launch counter tagging the exchange-table entries: read from device memory (the finalize kernel behind this launch
+  // bumps it) so that a captured CUDA graph advances by itself when replayed
+  const uint32_t epoch = p.epoch_ptr ? *p.epoch_ptr : p.epoch;
 
   // Work split.  tset = which set of corpus tiles this CTA (pair) walks; qblock = which 128 queries.
+  // With more than 256 queries in a launch, S = n_qblocks / 2 CTA pairs ("query super-blocks") walk the SAME tile set
+  // side by side, each with its own 256 queries in TMEM: the first pair to ask for a tile pulls it from HBM, its
+  // siblings hit L2, so the corpus crosses the HBM interface once per 256 * S queries instead of once per 256.
   int qblock, tset, n_tsets;
   if constexpr (kCtaGroup == 2) {
-    qblock = static_cast<int>(rank);
-    tset = blockIdx.x >> 1;
-    n_tsets = gridDim.x >> 1;
+    const int n_super = p.n_qblocks >> 1, pair = blockIdx.x >> 1;
+    qblock = (pair % n_super) * 2 + static_cast<int>(rank);
+    tset = pair / n_super;
+    n_tsets = (gridDim.x >> 1) / n_super;
   } else {
     qblock = blockIdx.x % p.n_qblocks;
     tset = blockIdx.x / p.n_qblocks;
@@ -284,10 +301,10 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   // exchange geometry: R-th largest of the m-th best of `nuse` CTAs is a valid threshold
   const int ksel = p.ksel;
   const int nuse = min(n_tsets, 96);
-  const int xm = (ksel <= nuse) ? 1 : 2;
+  const int xm = (ksel + nuse - 1) / nuse;            // rows every publishing CTA vouches for (1 .. 4)
   const int xR = (ksel + xm - 1) / xm;
   // (only CTAs that own at least one tile ever publish)
-  const bool xchg = (p.pub != nullptr) && (xR <= min(nuse, p.n_tiles));
+  const bool xchg = (p.pub != nullptr) && xm <= 4 && (xR <= min(nuse, p.n_tiles));
 
   if constexpr (kCtaGroup == 2) cluster_sync_all();  // both CTAs resident before the paired TMEM alloc
 
@@ -320,7 +337,8 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   if (warp == kProducerWarp) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
-      const uint64_t hint = (kCtaGroup == 2 || p.n_qblocks == 1) ? kEvictFirst : kEvictNormal;
+      // read once -> evict first; shared with sibling CTAs (two single CTAs or several query super-blocks) -> keep in L2
+      const uint64_t hint = ((kCtaGroup == 2 && p.n_qblocks == 2) || p.n_qblocks == 1) ? kEvictFirst : kEvictNormal;
       int stage = 0; uint32_t phase = 0;
       bool q_done = p.num_stages < 2 * kQStageBufs;   // too few stages: the query load does not borrow any
       long long tp_wait = 0;
@@ -447,7 +465,10 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     if (warp < kThrWarps) {
       // ============================== threshold warp ==============================
       // Serve the queries r = tset, tset + n_tsets, ... of this CTA's query block.
-      float cur[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      constexpr int kSlots = 8;                      // queries one CTA may have to serve: ceil(128 / tile sets), tile sets >= 16
+      float cur[kSlots];
+#pragma unroll
+      for (int sl = 0; sl < kSlots; ++sl) cur[sl] = -INFINITY;
       int polls = 0;
       while (xchg && my_tiles > 0) {
         // every epilogue thread of the grid waits for the FIRST threshold (bootstrap): poll fast until it is out
@@ -458,21 +479,21 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         unsigned long long cached[kTcQRows / 32];
 #pragma unroll
         for (int j = 0; j < kTcQRows / 32; ++j) cached[j] = __ldcg(thr_base + j * 32 + lane);
-        PubEntries ent[4];
+        PubEntries ent[kSlots];
         int nslot = 0;
 #pragma unroll
-        for (int sl = 0; sl < 4; ++sl) {
+        for (int sl = 0; sl < kSlots; ++sl) {
           const int rq = tset + sl * n_tsets;
           if (rq < kTcQRows) { ent[sl] = exchange_load(pub_base + static_cast<size_t>(rq) * pub_stride, nuse, lane); nslot = sl + 1; }
         }
 #pragma unroll
-        for (int sl = 0; sl < 4; ++sl) {
+        for (int sl = 0; sl < kSlots; ++sl) {
           if (sl < nslot) {
             const int rq = tset + sl * n_tsets;
-            const float t = exchange_select(ent[sl], nuse, xR, p.epoch, lane);
+            const float t = exchange_select(ent[sl], nuse, xR, epoch, lane);
             if (t > cur[sl]) {
               cur[sl] = t;
-              if (lane == 0) __stcg(thr_base + rq, (static_cast<unsigned long long>(p.epoch) << 32) | __float_as_uint(t));
+              if (lane == 0) __stcg(thr_base + rq, (static_cast<unsigned long long>(epoch) << 32) | __float_as_uint(t));
             }
           }
         }
@@ -480,7 +501,7 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         // memory once per tile; a global (L2) read there sat on the per-tile critical path with its full latency.
 #pragma unroll
         for (int j = 0; j < kTcQRows / 32; ++j)
-          if (static_cast<uint32_t>(cached[j] >> 32) == p.epoch) tau_s[j * 32 + lane] = __uint_as_float(static_cast<uint32_t>(cached[j]));   // only ever rises
+          if (static_cast<uint32_t>(cached[j] >> 32) == epoch) tau_s[j * 32 + lane] = __uint_as_float(static_cast<uint32_t>(cached[j]));   // only ever rises
         if (done) break;
       }
     } else {
@@ -524,30 +545,36 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
           const int n_j = (kbs - grp + kEpiGroups - 1) / kEpiGroups;      // k-blocks this group loads
           const int rot = n_j > 0 ? tset % n_j : 0;
           auto kb_of = [&](int j) { return (j < n_j) ? grp + ((j + rot) % n_j) * kEpiGroups : kbs; };
-          uint4 xa[8], xb[8];
-          load_kb(kb_of(0), xa);
-          for (int j = 0; j < n_j; ++j) {
-            const int kb = kb_of(j);
-            load_kb(kb_of(j + 1), xb);                        // next k-block in flight
-            if (kb < kTcTmemDim / kTcKBlock) {
-              uint8_t* buf = stg + (j % kBufs) * 4096;
-              if (kBufs == 1) __syncwarp();
-              scatter_kb(buf, xa);
-              __syncwarp();
-              uint32_t v[2][16];
+          // four k-blocks of loads (32 x 16 B per lane) are issued before the first is consumed: the block is read
+          // in three L2 round trips instead of twelve
+          constexpr int kDepth = 4;
+          uint4 x[kDepth][8];
+          for (int j0 = 0; j0 < n_j; j0 += kDepth) {
 #pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const uint4 t = *reinterpret_cast<const uint4*>(buf + lane * 128 + ((c ^ (lane & 7)) << 4));
-                v[c >> 2][(c & 3) * 4 + 0] = t.x; v[c >> 2][(c & 3) * 4 + 1] = t.y;
-                v[c >> 2][(c & 3) * 4 + 2] = t.z; v[c >> 2][(c & 3) * 4 + 3] = t.w;
+            for (int u = 0; u < kDepth; ++u) load_kb(kb_of(j0 + u), x[u]);
+#pragma unroll
+            for (int u = 0; u < kDepth; ++u) {
+              const int j = j0 + u;
+              if (j >= n_j) break;
+              const int kb = kb_of(j);
+              if (kb < kTcTmemDim / kTcKBlock) {
+                uint8_t* buf = stg + (j % kBufs) * 4096;
+                if (kBufs == 1) __syncwarp();
+                scatter_kb(buf, x[u]);
+                __syncwarp();
+                uint32_t v[2][16];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  const uint4 t = *reinterpret_cast<const uint4*>(buf + lane * 128 + ((c ^ (lane & 7)) << 4));
+                  v[c >> 2][(c & 3) * 4 + 0] = t.x; v[c >> 2][(c & 3) * 4 + 1] = t.y;
+                  v[c >> 2][(c & 3) * 4 + 2] = t.z; v[c >> 2][(c & 3) * 4 + 3] = t.w;
+                }
+                tmem_st_x16(lane_addr + kb * 32, v[0]);
+                tmem_st_x16(lane_addr + kb * 32 + 16, v[1]);
+              } else {
+                scatter_kb(smem + L.off_qs + static_cast<uint32_t>(kb - kTcTmemDim / kTcKBlock) * (kTcQRows * 128u) + quarter * 32 * 128, x[u]);
               }
-              tmem_st_x16(lane_addr + kb * 32, v[0]);
-              tmem_st_x16(lane_addr + kb * 32 + 16, v[1]);
-            } else {
-              scatter_kb(smem + L.off_qs + static_cast<uint32_t>(kb - kTcTmemDim / kTcKBlock) * (kTcQRows * 128u) + quarter * 32 * 128, xa);
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) xa[i] = xb[i];
           }
         } else {   // hardly any ring (large k at dim > 768): every thread fetches its own row
           const uint4* src = reinterpret_cast<const uint4*>(p.q + static_cast<size_t>(qglob) * p.dim);
@@ -584,16 +611,17 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       }
       float* mynorm = normbuf + (warp - kThrWarps) * 2 * kTcTileN;
       const uint32_t list_a = smem_u32(smem + L.off_list) + (static_cast<uint32_t>(grp) * L.lcap * kTcQRows + r) * 8u;
-      // deferred-candidate FIFO (see drain_fifo); only with one published value per CTA (xm == 1)
-      const bool use_fifo = L.fifo_recs > 0 && xm == 1;
+      // deferred-candidate FIFO (see drain_fifo) whenever shared memory has room for it
+      const bool use_fifo = L.fifo_recs > 0;
       const uint32_t fifo_a = smem_u32(smem + L.off_fifo) + r * 16u;
       const uint32_t ftag_a = smem_u32(smem + L.off_fifo) + L.fifo_recs * kTcQRows * 16u + r * 4u;
       int fcnt = 0;
       TopkState st;
       st.min_key = kKeyEmpty; st.tau_local = -INFINITY; st.tau = -INFINITY;
-      st.top1 = -INFINITY; st.top2 = -INFINITY; st.minpos = 0; st.nfill = 0;
+      st.top[0] = st.top[1] = st.top[2] = st.top[3] = -INFINITY; st.minpos = 0; st.nfill = 0;
       if (qglob >= p.nq) st.tau = INFINITY;   // padding row of a partial query block: admits nothing, appends nothing
       float published = -INFINITY;
+      bool booted = false;   // the bootstrap has already fed the first tile's chunk maxima into st.top
       int nslow = 0;
       long long t_wait = 0, t_slow = 0, t_ld = 0, t_top = 0, t_fast = 0, t_chunks = 0, t_pub = 0;
       const long long t_begin = TCLK();
@@ -623,27 +651,22 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       if (xchg && grp < my_tiles) {
         mbar_wait(&tmem_full[grp & 1], 0);
         tc_fence_after();
-        float t1 = -INFINITY, t2 = -INFINITY;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t a16[16];
           tmem_ld_x16(lane_addr + kTcAccCol0 + (grp & 1) * kTcTileN + c * 16, a16);
           tmem_wait_ld();
+          float m = -INFINITY;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float sc = __uint_as_float(a16[j]) * mynorm[c * 16 + j];
-            if (sc > t1) { t2 = t1; t1 = sc; } else if (sc > t2) t2 = sc;
-          }
+          for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(a16[j]) * mynorm[c * 16 + j]);
+          top4_insert(st.top, m);       // (the main loop skips the tracker for this tile: it is counted here)
         }
-        const float pv0 = (xm == 1) ? t1 : t2;
+        const float pv0 = top4_get(st.top, xm);
         if (pv0 > -INFINITY) {
           published = pv0;
-          atomicMax(pubrow + tset, (static_cast<unsigned long long>(p.epoch) << 32) | f32_to_ord(pv0));
+          atomicMax(pubrow + tset, (static_cast<unsigned long long>(epoch) << 32) | f32_to_ord(pv0));
         }
-        // The main loop examines this tile again.  Only the FIFO mode may keep t1 (there top1 is an idempotent
-        // running max); the push path counts every admitted row into top1 / top2, so seeding them here would
-        // count the tile's best row twice and publish it as "second best" -- an unsound threshold when xm == 2.
-        if (L.fifo_recs > 0 && xm == 1) st.top1 = t1;
+        booted = true;
         const long long tb = clock64();
         float tboot = -INFINITY;
         do {
@@ -722,12 +745,16 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         }
 
         t_fast += TCLK() - t_fast0;
-        if (p.dbg_flags & 8) { st.top1 = fmaxf(st.top1, fmaxf(fmaxf(cmax[0], cmax[1]), fmaxf(cmax[2], cmax[3]))); continue; }
+        // what this CTA can vouch for (published below): chunk maxima are distinct rows
+        if (!(booted && li == 0)) {
+          if (xm == 1) st.top[0] = fmaxf(st.top[0], fmaxf(fmaxf(cmax[0], cmax[1]), fmaxf(cmax[2], cmax[3])));
+          else { top4_insert(st.top, cmax[0]); top4_insert(st.top, cmax[1]); top4_insert(st.top, cmax[2]); top4_insert(st.top, cmax[3]); }
+        }
+        if (p.dbg_flags & 8) continue;
         const long long t_ch0 = TCLK();
         // A group of four scores whose max reaches this query's threshold goes out of line.
         st.tau = fmaxf(st.tau, thr_now);
         if (use_fifo) {
-          st.top1 = fmaxf(st.top1, fmaxf(fmaxf(cmax[0], cmax[1]), fmaxf(cmax[2], cmax[3])));   // published below
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             if (cmax[c] >= st.tau) {
@@ -773,10 +800,10 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         if (li < 8) t_top += TCLK() - t_ch0; else t_chunks += TCLK() - t_ch0;   // t_top reused: early tiles
         const long long t_pub0 = TCLK();
         // publish this CTA's m-th best for the exchange (monotone, so stale reads stay valid)
-        const float pv = (xm == 1) ? st.top1 : st.top2;
+        const float pv = top4_get(st.top, xm);
         if (xchg && pv > published) {
           published = pv;
-          atomicMax(pubrow + tset, (static_cast<unsigned long long>(p.epoch) << 32) | f32_to_ord(pv));
+          atomicMax(pubrow + tset, (static_cast<unsigned long long>(epoch) << 32) | f32_to_ord(pv));
         }
         t_pub += TCLK() - t_pub0;
       }
@@ -785,7 +812,7 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       if (lane == 0) atomicAdd(const_cast<int*>(epi_done), 1);   // lets the threshold warps go
       if (use_fifo) {   // whatever is still parked meets the final threshold below
         float tau_fin = -INFINITY;
-        if (xchg && my_tiles > 0) tau_fin = read_threshold(thr_q, p.epoch);
+        if (xchg && my_tiles > 0) tau_fin = read_threshold(thr_q, epoch);
         st.tau = fmaxf(st.tau, tau_fin);
         if (__any_sync(0xffffffffu, fcnt > 0)) st = drain_fifo(st, fifo_a, ftag_a, fcnt, list_a, ksel);
         fcnt = 0;
@@ -794,7 +821,7 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       // ---- append the survivors (score >= the certified threshold, at most ksel of them)
       //      to this query's compact candidate row
       float tau_end = -INFINITY;
-      if (xchg && my_tiles > 0) tau_end = read_threshold(thr_q, p.epoch);
+      if (xchg && my_tiles > 0) tau_end = read_threshold(thr_q, epoch);
       st.tau = fmaxf(st.tau, tau_end);
       st = compact_list(st, list_a, ksel);
       {

@@ -175,6 +175,28 @@ class ShardedIndex:
             self.index.search_dev(q.data_ptr(), nq, k, b["s"].data_ptr(), b["i"].data_ptr(), stream=s)
         return b["i"], b["s"]
 
+    def capture(self, q, k: int):
+        """The whole step (local search -> peer stores -> merge) as ONE CUDA graph: ``replay()`` costs a single launch
+        and the three kernels run back to back with no host in between.  Possible because every per-launch counter of
+        the step (exchange-table epoch, exchange sequence number, candidate counts) lives in device memory and is
+        advanced by the kernels themselves.  Returns (replay, ids, scores); all ranks must replay in lock step."""
+        import torch
+
+        if self.exchange == "nccl":
+            raise RuntimeError("capture() covers the fused exchange and the single-GPU step, not the NCCL variant")
+        side = torch.cuda.Stream(device=self._dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):                       # sizes every scratch buffer of this stream's search context
+                self.search(q, k, stream=side.cuda_stream)
+        side.synchronize()
+        if self.dist is not None and self.world > 1:
+            self.dist.barrier()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+            ids, sc = self.search(q, k, stream=side.cuda_stream)
+        return g.replay, ids, sc
+
     def close(self) -> None:
         if self._fx is not None:
             self._fx.close()

@@ -290,6 +290,13 @@ def run_search(args, name: str):
     for _ in range(max(args.warmup, 3)):
         step_dev()
     _barrier(torch, dist, world)
+    step_timed = step_dev
+    if args.graph:          # the step as one CUDA graph (one launch per step)
+        replay, g_ids, g_sc = sh.capture(q_dev, k)
+        step_timed = replay
+        for _ in range(3):
+            replay()
+        _barrier(torch, dist, world)
 
     # ---- value: K steps, queries resident in HBM, CUDA events on the launching stream
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -297,7 +304,7 @@ def run_search(args, name: str):
         _barrier(torch, dist, world)
         e0.record()
         for _ in range(args.steps):
-            step_dev()
+            step_timed()
         e1.record()
         _barrier(torch, dist, world)
         # keep the sampler running a little so short runs still get a few samples under load
@@ -325,6 +332,11 @@ def run_search(args, name: str):
     phases = {a: float(np.median(b)) for a, b in ph.items()}
     kernel_ms = phases["kernel_ms"]
     kernel_name = N.KERNEL_NAMES[st["last_kernel"]]
+    if args.graph:          # the answer that gets checked is the graph replay's
+        _barrier(torch, dist, world)
+        replay()
+        torch.cuda.synchronize()
+        out_i, out_s = g_ids, g_sc
     got_ids, got_sc = out_i.cpu().numpy(), out_s.cpu().numpy()
     if world > 1:     # every rank must hold the same merged answer
         ref = out_i.clone()
@@ -408,7 +420,8 @@ def run_search(args, name: str):
         "config": {"workload": cfg["workload"], "nq": nq, "rows": n_total, "rows_per_gpu": n_local, "dim": dim, "k": k,
                    "parallelism": f"row-shard x{world}",
                    "l2": f"shard ({n_local * dim * 2 / 1e6:.0f} MB) vs L2 (126 MB): " + ("larger, no flush needed" if n_local * dim * 2 > 2.5e8 else "NOT much larger than L2 at this N"),
-                   "kernel": kernel_name, "exchange": exch},
+                   "kernel": kernel_name, "exchange": exch,
+                   "launch": "one CUDA graph per step (search + exact re-rank + exchange/merge captured once)" if args.graph else "stream launches"},
         "e2e": {"value": e2e, "unit": "queries/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": nq * dim * 2, "d2h_bytes_per_step": nq * k * 12},
         "gpu_launches": launches * args.steps,
@@ -779,6 +792,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"], help="cross-shard step at N > 1")
+    ap.add_argument("--graph", action="store_true", help="replay the step as one captured CUDA graph (cfg2 / cfg4)")
     ap.add_argument("--no-encoder", action="store_true", help="skip the encoder leg of the N=1 cfg2 run")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run oracle check (timing experiments only)")
     args = ap.parse_args()

@@ -76,6 +76,8 @@ CASES = [
     # the real architectures at a few short sequences (outputs only: weights are re-seeded by the tests)
     ("minilm_l6", B.MINILM_L6, 3, 14, dict(mean_len=24, std_len=8, min_len=4, max_len=48)),
     ("bge_base", B.BGE_BASE, 2, 15, dict(mean_len=24, std_len=8, min_len=4, max_len=48)),
+    # cfg4's 1024-d vectors come from this architecture (H1024 L24 A16 I4096)
+    ("bge_large", B.BGE_LARGE, 2, 16, dict(mean_len=24, std_len=8, min_len=4, max_len=48)),
 ]
 
 

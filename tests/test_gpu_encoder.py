@@ -24,7 +24,10 @@ from aurora_b200.engine import Index, to_bf16_bits
 from oracle import bert_encoder as B
 from oracle.cosine_topk import bf16_bits_to_f32, round_to_bf16
 
-COS_TOL, ABS_TOL = 0.9995, 1e-2
+# Floating-point tolerance of the encoder path (bf16 activations between kernels, fp32 accumulation) against the fp64
+# oracle on the same bf16-rounded weights: pooled unit vectors must agree to cosine >= 0.9999 and 4e-3 per component
+# (measured on B200: 0.99993 / 2.1e-3 at bge-base dims; a regression of either shows up here).
+COS_TOL, ABS_TOL = 0.9999, 4e-3
 
 
 def _ptr(a):
@@ -92,6 +95,7 @@ def test_attention_matches_numpy(heads, lens):
 
 def _check_pooled(got, ref):
     cos = (got * ref).sum(axis=1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(ref, axis=1))
+    print(f"pooled parity: min cosine {cos.min():.6f}, max |d| {np.abs(got - ref).max():.2e}")     # (pytest -s / on failure)
     assert cos.min() >= COS_TOL, cos.min()
     assert np.abs(got - ref).max() <= ABS_TOL, np.abs(got - ref).max()
 
@@ -125,6 +129,24 @@ def test_bge_base_matches_hf_golden():
         enc.load_weights(w)
         got = enc.encode_packed(np.asarray(case["tokens"], np.int32), np.asarray(case["cu_seqlens"], np.int32))
     _check_pooled(got, np.asarray(case["pooled"]))
+
+
+def test_bge_large_matches_hf_golden():
+    """bge-large-en architecture (H1024 / L24 / 16 heads / I4096: the encoder behind BASELINE config 4's 1024-d vectors),
+    random-init, against transformers.BertModel's output, then a longer ragged batch against the oracle."""
+    with open(os.path.join(os.path.dirname(__file__), "golden", "bert_ref.json")) as f:
+        case = next(c for c in json.load(f)["cases"] if c["name"] == "bge_large")
+    cfg_o = B.BertConfig(**case["cfg"])
+    assert (cfg_o.hidden, cfg_o.layers, cfg_o.heads, cfg_o.inter) == (1024, 24, 16, 4096)
+    w = B.init_weights(cfg_o, seed=7, bf16=True)
+    with Encoder(_mirror(cfg_o), max_tokens=4096, max_seqs=8) as enc:
+        enc.load_weights(w)
+        got = enc.encode_packed(np.asarray(case["tokens"], np.int32), np.asarray(case["cu_seqlens"], np.int32))
+        _check_pooled(got, np.asarray(case["pooled"]))
+        tok, cu = B.synth_batch(cfg_o, 3, 44, mean_len=120, std_len=60, min_len=8, max_len=300)
+        got2 = enc.encode_packed(tok, cu)
+        assert enc.stats()["launches"] == 2 + 7 * 24
+    _check_pooled(got2, B.encode(cfg_o, w, tok, cu, dtype=np.float32).astype(np.float64))
 
 
 def test_minilm_l6_matches_hf_golden():

@@ -127,6 +127,9 @@ def test_uniform_tenant_scope_is_served_by_the_tcgen05_kernel(with_org):
     (777, 64, 1, 1), (12345, 256, 129, 128), (64, 768, 256, 32), (5000, 768, 128, 64),
     # dims past 768: the first 768 dims of the queries sit in TMEM, the rest in shared memory (SS MMAs)
     (20000, 1024, 256, 32), (9000, 1024, 300, 64), (7000, 896, 130, 10), (4000, 832, 64, 5),
+    # more than 256 queries per launch: several CTA pairs ("query super-blocks") walk the same tiles side by side, fewer
+    # tile sets, so every CTA vouches for 2-4 rows in the threshold exchange
+    (40000, 768, 1024, 32), (30000, 768, 600, 10), (25000, 1024, 1024, 100), (60000, 768, 512, 32), (3000, 768, 900, 64),
 ])
 def test_tcgen05_parity(kernel, n, d, nq, k):
     C, Q = _data(n, d, nq, seed=n % 1000 + nq + d)
