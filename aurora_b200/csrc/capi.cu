@@ -126,13 +126,15 @@ struct SearchCtx {
   DevBuf<float> score_chunk;
   DevBuf<float> masked_inv;      // inverse norms with the invisible rows turned into NaN (tenant scope / id subset)
   DevBuf<int32_t> allow_rows;    // subset search: rows that stay visible
+  DevBuf<uint32_t> row_mask;     // per-query tenant scopes on the tensor path: bit s = scope s of the batch sees the row
+  DevBuf<int32_t> scope_tab, q_scope;   // the batch's distinct {user, org} scopes (<= 32) and every query's scope index
   DevBuf<uint8_t> stage_q;       // host-entry staging: queries
   DevBuf<int32_t> stage_quser, stage_qorg;
   DevBuf<float> stage_scores;
   DevBuf<int64_t> stage_ids;
   void release() {
     cand_a.release(); cand_b.release(); pub.release(); cand_count.release(); d_epoch.release(); score_chunk.release(); masked_inv.release();
-    allow_rows.release(); stage_q.release(); stage_quser.release(); stage_qorg.release(); stage_scores.release();
+    allow_rows.release(); row_mask.release(); scope_tab.release(); q_scope.release(); stage_q.release(); stage_quser.release(); stage_qorg.release(); stage_scores.release();
     stage_ids.release();
     if (ev_begin) cudaEventDestroy(ev_begin);
     if (ev_k0) cudaEventDestroy(ev_k0);
@@ -236,7 +238,8 @@ void release_ctx(aur_index* ix, SearchCtx* c) {
 // Runs one block of <= 256 queries through the tcgen05 kernel over the first n_rows rows.  Leaves candidate keys
 // in c->cand_a as [nqb_pad, n_lists, ksel]; returns n_lists.
 int run_tc_block(aur_index* ix, SearchCtx* c, int cta_group, const void* q_dev, int nqb, int ksel, int64_t n_rows, float* dbg,
-                 int* n_lists_out, cudaStream_t s, const float* inv_norm = nullptr) {
+                 int* n_lists_out, cudaStream_t s, const float* inv_norm = nullptr, const uint32_t* row_mask = nullptr,
+                 const int32_t* q_scope = nullptr) {
   int n_qblocks = (nqb > kTcQRows) ? 2 : 1;
   if (cta_group == 2 && n_qblocks != 2) {
     // a pair works on 256 query rows.  A short tail block normally runs as single CTAs; when their larger
@@ -281,6 +284,7 @@ int run_tc_block(aur_index* ix, SearchCtx* c, int cta_group, const void* q_dev, 
   TcParams p;
   p.q = static_cast<const __nv_bfloat16*>(q_dev);
   p.inv_norm = inv_norm ? inv_norm : ix->d_inv_norm;
+  p.row_mask = row_mask; p.q_scope = q_scope;
   p.cand = c->cand_a.p;
   p.cand_count = c->cand_count.p;
   p.dbg_scores = dbg;
@@ -308,6 +312,9 @@ struct Scope {
   const int32_t* uniform = nullptr;      // host {user, org}: every query of the batch carries this scope
   const int32_t* allow_rows = nullptr;   // device: rows that stay visible (subset search)
   int64_t n_allow = -1;                  // -1 = no subset
+  const int32_t* scope_tab = nullptr;    // device [n_scopes][2]: the batch's distinct tenant scopes, when there are <= 32
+  const int32_t* q_scope = nullptr;      // device [nq]: scope index of every query
+  int n_scopes = 0;
 };
 
 // Enqueues one search over the published prefix `n_rows` on stream s using context c.
@@ -318,7 +325,8 @@ int search_enqueue(aur_index* ix, SearchCtx* c, const void* q_dev, int nq, int k
   if (k > kMaxK) return fail(AUR_ERR_UNSUPPORTED, "k > %d", kMaxK);
   if (nq > 65535) return fail(AUR_ERR_UNSUPPORTED, "nq > 65535: split the batch");
   const bool subset = sc.n_allow >= 0;
-  const bool filtered = sc.q_user != nullptr && sc.uniform == nullptr && !subset;   // per-query scopes: generic kernel only
+  const bool scoped_tc = sc.n_scopes > 0 && !subset && sc.uniform == nullptr;        // per-query scopes through bit masks
+  const bool filtered = sc.q_user != nullptr && sc.uniform == nullptr && !subset && !scoped_tc;   // else: generic kernel only
   const int ksel = k + kSlack;
   int kernel = ix->opt_kernel;
   if (kernel == AUR_KERNEL_AUTO) kernel = tc_shape_ok(ix, k, filtered) ? AUR_KERNEL_TC2 : AUR_KERNEL_SIMT;
@@ -337,7 +345,11 @@ int search_enqueue(aur_index* ix, SearchCtx* c, const void* q_dev, int nq, int k
     CU_TRY(launch_scatter_inv_norm(ix->d_inv_norm, sc.allow_rows, sc.n_allow, n_rows, c->masked_inv.p, s));
     c->last_launches += 2;
     inv = c->masked_inv.p;
-  } else if (kernel != AUR_KERNEL_SIMT && sc.q_user != nullptr && n_rows > 0) {   // one scope for the whole batch
+  } else if (kernel != AUR_KERNEL_SIMT && scoped_tc && n_rows > 0) {              // up to 32 scopes in the batch: row bit masks
+    CU_TRY(c->row_mask.reserve(static_cast<size_t>(ix->capacity) + 64));
+    CU_TRY(launch_row_scope_mask(ix->d_user, ix->d_org, sc.scope_tab, sc.n_scopes, n_rows, c->row_mask.p, s));
+    ++c->last_launches;
+  } else if (kernel != AUR_KERNEL_SIMT && sc.q_user != nullptr && sc.uniform != nullptr && n_rows > 0) {   // one scope for the whole batch
     CU_TRY(c->masked_inv.reserve(static_cast<size_t>(ix->capacity) + 64));
     CU_TRY(launch_mask_inv_norm(ix->d_inv_norm, ix->d_user, ix->d_org, sc.uniform[0], sc.uniform[1], n_rows, c->masked_inv.p, s));
     ++c->last_launches;
@@ -370,7 +382,7 @@ int search_enqueue(aur_index* ix, SearchCtx* c, const void* q_dev, int nq, int k
         const int64_t chunk = 16 * kSimtSeg;  // 32768 rows of scores at a time
         CU_TRY(c->score_chunk.reserve(static_cast<size_t>(nqb) * chunk));
         FilterArgs f{ix->d_user, ix->d_org, nullptr, nullptr};
-        if (!subset && sc.q_user) { f.q_user = sc.q_user + q0; f.q_org = sc.q_org ? sc.q_org + q0 : nullptr; }
+        if (!subset && sc.q_user && !inv) { f.q_user = sc.q_user + q0; f.q_org = sc.q_org ? sc.q_org + q0 : nullptr; }
         if (!k_timed) CU_TRY(cudaEventRecord(c->ev_k0, s));
         for (int64_t r0 = 0; r0 < n_rows; r0 += chunk) {
           const int64_t nr = (n_rows - r0 < chunk) ? n_rows - r0 : chunk;
@@ -385,7 +397,9 @@ int search_enqueue(aur_index* ix, SearchCtx* c, const void* q_dev, int nq, int k
       cur = c->cand_a.p;
     } else {
       if (!k_timed) CU_TRY(cudaEventRecord(c->ev_k0, s));
-      int rc = run_tc_block(ix, c, kernel == AUR_KERNEL_TC1 ? 1 : 2, qb, nqb, ksel, n_rows, nullptr, &n_lists, s, inv);
+      const bool use_mask = scoped_tc && n_rows > 0;
+      int rc = run_tc_block(ix, c, kernel == AUR_KERNEL_TC1 ? 1 : 2, qb, nqb, ksel, n_rows, nullptr, &n_lists, s, inv,
+                            use_mask ? c->row_mask.p : nullptr, use_mask ? sc.q_scope + q0 : nullptr);
       if (rc != AUR_OK) return rc;
       if (!k_timed) { CU_TRY(cudaEventRecord(c->ev_k1, s)); k_timed = true; }
       c->last_launches += 1;
@@ -414,7 +428,7 @@ int search_enqueue(aur_index* ix, SearchCtx* c, const void* q_dev, int nq, int k
     fa.out_scores = scores ? scores + static_cast<size_t>(q0) * k : nullptr;
     fa.out_ids = ids ? ids + static_cast<size_t>(q0) * k : nullptr;
     fa.out_scores64 = scores64 ? scores64 + static_cast<size_t>(q0) * k : nullptr;
-    if (ex) { fa.ex = *ex; fa.ex.q0 = q0; fa.ex.signal = (q0 + qstep >= nq) ? ex->signal : 0; }   // only the last launch signals
+    if (ex) { fa.ex = *ex; fa.ex.q0 = q0; }
     CU_TRY(launch_finalize(fa, s));
     c->last_launches += 1;
   }
@@ -529,6 +543,29 @@ int search_host(aur_index* ix, const void* queries_host, int32_t nq, int32_t k, 
     scope[0] = q_user[0]; scope[1] = q_org ? q_org[0] : -1;
     for (int i = 1; i < nq && uniform; ++i) uniform = q_user[i] == scope[0] && (q_org ? q_org[i] : -1) == scope[1];
     if (uniform) sc.uniform = scope;
+    else {
+      // a coalesced batch of several tenants' questions: with at most 32 distinct scopes every corpus row gets a bit
+      // mask (one pre-pass) and the tensor-core kernel serves the batch; more scopes -> the generic kernel
+      std::vector<int32_t> tab; std::vector<int32_t> qs(static_cast<size_t>(nq));
+      bool fits = true;
+      for (int i = 0; i < nq && fits; ++i) {
+        const int32_t u = q_user[i], o = q_org ? q_org[i] : -1;
+        int found = -1;
+        for (size_t t = 0; t < tab.size() / 2; ++t) if (tab[2 * t] == u && tab[2 * t + 1] == o) { found = static_cast<int>(t); break; }
+        if (found < 0) {
+          if (tab.size() / 2 == 32) { fits = false; break; }
+          found = static_cast<int>(tab.size() / 2); tab.push_back(u); tab.push_back(o);
+        }
+        qs[static_cast<size_t>(i)] = found;
+      }
+      if (fits) {
+        CU_TRY(c->scope_tab.reserve(64)); CU_TRY(c->q_scope.reserve(static_cast<size_t>(nq)));
+        CU_TRY(cudaMemcpyAsync(c->scope_tab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(c->q_scope.p, qs.data(), static_cast<size_t>(nq) * 4, cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaStreamSynchronize(s));          // tab / qs are host temporaries
+        sc.scope_tab = c->scope_tab.p; sc.q_scope = c->q_scope.p; sc.n_scopes = static_cast<int>(tab.size() / 2);
+      }
+    }
   }
   rc = search_enqueue(ix, c, c->stage_q.p, nq, k, sc, n_rows, c->stage_scores.p, c->stage_ids.p, nullptr, s);
   if (rc != AUR_OK) { cudaStreamSynchronize(s); return rc; }
@@ -832,7 +869,7 @@ int aur_search_subset(aur_index* ix, const void* queries_host, int32_t nq, int32
 // round trip: local search -> peer stores -> merge is three kernels on one stream.
 struct aur_exchange {
   int device = 0, rank = 0, world = 1, nq_max = 0, k_max = 0;
-  size_t plane = 0, slot_stride = 0, parity_stride = 0, flags_off = 0, bytes = 0;   // in 8-byte words (bytes: bytes)
+  size_t entries = 0, slot_stride = 0, parity_stride = 0, bytes = 0;   // slot_stride / parity_stride in 8-byte words
   uint64_t* local = nullptr;           // this rank's buffer (cudaMalloc, exported through cudaIpc)
   uint64_t* peer[8] = {};              // every rank's buffer as mapped here (peer[rank] == local)
   uint64_t* d_seq = nullptr;           // exchanges completed
@@ -876,11 +913,10 @@ int aur_exchange_create(int32_t device, int32_t rank, int32_t world, int32_t nq_
   CU_TRY(cudaSetDevice(device));
   aur_exchange* ex = new aur_exchange();
   ex->device = device; ex->rank = rank; ex->world = world; ex->nq_max = nq_max; ex->k_max = k_max;
-  ex->plane = static_cast<size_t>(nq_max) * k_max;
-  ex->slot_stride = 2 * ex->plane;
+  ex->entries = static_cast<size_t>(nq_max) * k_max;
+  ex->slot_stride = 4 * ex->entries;                       // an entry = 4 tagged words (score lo / hi, id lo / hi)
   ex->parity_stride = static_cast<size_t>(world) * ex->slot_stride;
-  ex->flags_off = 2 * ex->parity_stride;
-  ex->bytes = (ex->flags_off + 2 * static_cast<size_t>(world) + 16) * 8;
+  ex->bytes = 2 * ex->parity_stride * 8 + 256;
   cudaError_t e = cudaMalloc(&ex->local, ex->bytes);
   if (e == cudaSuccess) e = cudaMemset(ex->local, 0, ex->bytes);
   if (e == cudaSuccess) e = cudaMalloc(&ex->d_seq, 8);
@@ -945,7 +981,7 @@ int aur_search_exchange_dev(aur_index* ix, aur_exchange* ex, const void* queries
   if (rc != AUR_OK) return rc;
   if (!ex || !ex->connected) return fail(AUR_ERR_INVALID, "exchange not connected");
   if (ex->device != ix->device) return fail(AUR_ERR_INVALID, "exchange and index live on different devices");
-  if (nq > ex->nq_max || k > ex->k_max || static_cast<size_t>(nq) * k > ex->plane)
+  if (nq > ex->nq_max || k > ex->k_max || static_cast<size_t>(nq) * k > ex->entries)
     return fail(AUR_ERR_INVALID, "batch %d x top-%d exceeds the exchange's %d x %d", nq, k, ex->nq_max, ex->k_max);
   std::shared_lock<std::shared_mutex> rl(ix->rw);
   CU_TRY(cudaSetDevice(ix->device));
@@ -958,21 +994,14 @@ int aur_search_exchange_dev(aur_index* ix, aur_exchange* ex, const void* queries
   for (int r = 0; r < ex->world; ++r) eo.slot[r] = ex->peer[r] + static_cast<size_t>(ex->rank) * ex->slot_stride;
   eo.seq = ex->d_seq;
   eo.parity_stride = ex->parity_stride;
-  eo.plane_stride = ex->plane;
-  for (int r = 0; r < ex->world; ++r) eo.flag[r] = ex->peer[r] + ex->flags_off + ex->rank;
-  eo.done = ex->d_done + 2;
-  eo.flag_parity_stride = ex->world;
-  eo.signal = 1;
   Scope sc;
   rc = search_enqueue(ix, c, queries_dev, nq, k, sc, ix->rows_pub.load(std::memory_order_acquire), nullptr, nullptr, nullptr, s, &eo);
   if (rc != AUR_OK) return rc;
   ExchangeParams p{};
-  p.slots = ex->local; p.flags = ex->local + ex->flags_off;
-  for (int r = 0; r < ex->world; ++r) p.peer_flags[r] = ex->peer[r] + ex->flags_off;
+  p.slots = ex->local;
   p.seq = ex->d_seq; p.done = ex->d_done; p.status = ex->d_done + 1;
   p.world = ex->world; p.rank = ex->rank; p.nq = nq; p.k = k;
-  p.signal = 0;     // the finalize kernel's last block raised the flags already
-  p.parity_stride = ex->parity_stride; p.slot_stride = ex->slot_stride; p.plane_stride = ex->plane;
+  p.parity_stride = ex->parity_stride; p.slot_stride = ex->slot_stride;
   p.out_scores = scores_dev; p.out_ids = ids_dev;
   CU_TRY(launch_exchange_merge(p, s));
   c->last_launches += 1;

@@ -52,6 +52,8 @@ constexpr int kMaxK = 128;
 struct TcParams {
   const __nv_bfloat16* q;   // [nq, dim] queries of this launch (<= 128 * n_qblocks)
   const float* inv_norm;    // [n_rows]   1/|c_j|, 0 for zero rows, NaN for tombstones
+  const uint32_t* row_mask; // nullable [n_rows]: bit s = tenant scope s of this batch may see the row (per-query scopes)
+  const int32_t* q_scope;   // with row_mask: [nq] scope index (0..31) of every query
   uint64_t* cand;           // [128 * n_qblocks, n_lists * ksel] candidate keys, compacted per
                             // query: only keys that pass the final threshold are appended
   uint32_t* cand_count;     // [128 * n_qblocks] appended keys per query (zero on entry)
@@ -109,34 +111,28 @@ struct FinalizeArgs {
   const int64_t* ids;
   float* out_scores; int64_t* out_ids; double* out_scores64;   // (out_scores / out_ids nullable in exchange mode)
   int sort_cap;      // set by launch_finalize: keys the shared sort buffer holds
-  // Fused cross-shard exchange (ExchangeOut.n_peers > 0): the exact (fp64 score, id) rows of this shard are
-  // stored straight into every rank's exchange buffer over NVLink instead of a local array + all-gather.
+  // Fused cross-shard exchange (ExchangeOut.n_peers > 0): the exact (fp64 score, id) rows of this shard are stored
+  // straight into every rank's exchange buffer over NVLink instead of a local array + all-gather.  Every 8-byte word
+  // that crosses carries 4 bytes of payload and a 4-byte tag (the exchange's sequence number), so a word is valid the
+  // moment its tag matches: 8-byte stores are single-copy atomic, the receiver polls the words themselves, and no
+  // flag, fence or counter sits on the critical path (the layout NCCL's LL protocol uses).  An entry = 4 words:
+  // score lo, score hi, id lo, id hi.
   struct ExchangeOut {
     uint64_t* slot[8];          // per destination rank: base of THIS rank's slot in that rank's buffer (parity 0)
     int n_peers;                // 0 = off
     const uint64_t* seq;        // device word: exchanges completed so far (this one is *seq + 1; parity = its low bit)
     size_t parity_stride;       // 8-byte words between the two parities of a buffer
-    size_t plane_stride;        // words between the score plane and the id plane of a slot
     int q0;                     // first query of this launch inside the batch
-    // delivery signal, raised by the last block of the LAST finalize launch of a search (signal != 0): flag[r] is this
-    // rank's entry (parity 0) in rank r's flag array; done counts finished blocks (self-resetting)
-    uint64_t* flag[8];
-    uint32_t* done;
-    int flag_parity_stride;     // words between the two parities of a flag array (= world)
-    int signal;
   } ex;
 };
-// Cross-shard merge fed by the peer stores above: signal every peer, wait for all of them, keep the best k.
+// Cross-shard merge fed by the peer stores above: poll the tagged words of all ranks' slots, keep the best k.
 struct ExchangeParams {
-  uint64_t* slots;              // this rank's buffer: [2 parity][world][2 planes][plane_stride]
-  uint64_t* flags;              // this rank's flags:  [2 parity][world]   (sequence number a peer has delivered)
-  uint64_t* peer_flags[8];      // the same array in every rank's buffer
+  uint64_t* slots;              // this rank's buffer: [2 parity][world][nq_max * k_max entries][4 words]
   uint64_t* seq;                // device word, bumped by the last block
   uint32_t* done;               // block counter (self-resetting)
   uint32_t* status;             // != 0: a peer did not deliver in time
   int world, rank, nq, k;
-  int signal;                   // != 0: this kernel raises the delivery flags itself (else the finalize kernel did)
-  size_t parity_stride, slot_stride, plane_stride;
+  size_t parity_stride, slot_stride;   // in words
   float* out_scores; int64_t* out_ids;
 };
 cudaError_t launch_exchange_merge(const ExchangeParams& p, cudaStream_t s);
@@ -147,6 +143,9 @@ cudaError_t launch_merge_topk(const double* in_s, const int64_t* in_ids, size_t 
 cudaError_t launch_cosine_pairs(const float* a, const float* b, int64_t n, int dim, int clamp, double* out,
                                 cudaStream_t s);
 cudaError_t launch_fill_f32(float* p, float v, int64_t n, cudaStream_t s);
+// out[i] = OR over the batch's distinct tenant scopes s < n_scopes of (visible(row i, scope s) << s); scopes = {user, org} pairs
+cudaError_t launch_row_scope_mask(const int32_t* row_user, const int32_t* row_org, const int32_t* scopes, int n_scopes, int64_t n,
+                                  uint32_t* out, cudaStream_t s);
 // out[i] = visible(user u, org o) ? inv[i] : NaN  -- lets the tcgen05 kernel serve a batch whose queries all
 // carry the same tenant scope
 cudaError_t launch_mask_inv_norm(const float* inv, const int32_t* row_user, const int32_t* row_org, int32_t u, int32_t o,

@@ -353,18 +353,23 @@ finalize_kernel(FinalizeArgs a) {
   }
   __syncthreads();
   // where a result row goes: local arrays and / or this rank's slot in every rank's exchange buffer (peer stores)
-  const uint64_t ex_par = (a.ex.n_peers > 0) ? (((*a.ex.seq + 1) & 1ull) * a.ex.parity_stride) : 0ull;
+  const uint64_t ex_seq = (a.ex.n_peers > 0) ? (*a.ex.seq + 1) : 0ull;
+  const uint64_t ex_par = (ex_seq & 1ull) * a.ex.parity_stride;
+  const uint64_t ex_tag = (ex_seq & 0xFFFFFFFFull) << 32;
   auto emit = [&](int pos, double s, int64_t id) {
     const size_t o = static_cast<size_t>(qi) * a.k + pos;
     if (a.out_scores) { a.out_scores[o] = static_cast<float>(s); a.out_ids[o] = id; }
     if (a.out_scores64) a.out_scores64[o] = s;
     if (a.ex.n_peers > 0) {
-      const size_t w = ex_par + static_cast<size_t>(a.ex.q0 + qi) * a.k + pos;
-      const uint64_t sb = static_cast<uint64_t>(__double_as_longlong(s));
+      const size_t w = ex_par + (static_cast<size_t>(a.ex.q0 + qi) * a.k + pos) * 4;
+      const uint64_t sb = static_cast<uint64_t>(__double_as_longlong(s)), ib = static_cast<uint64_t>(id);
+      const uint64_t w0 = ex_tag | (sb & 0xFFFFFFFFull), w1 = ex_tag | (sb >> 32);
+      const uint64_t w2 = ex_tag | (ib & 0xFFFFFFFFull), w3 = ex_tag | (ib >> 32);
 #pragma unroll 1
       for (int r = 0; r < a.ex.n_peers; ++r) {
-        a.ex.slot[r][w] = sb;
-        a.ex.slot[r][w + a.ex.plane_stride] = static_cast<uint64_t>(id);
+        ulonglong2* dst = reinterpret_cast<ulonglong2*>(a.ex.slot[r] + w);      // two 16-byte stores (each word valid on its own)
+        dst[0] = make_ulonglong2(w0, w1);
+        dst[1] = make_ulonglong2(w2, w3);
       }
     }
   };
@@ -383,19 +388,6 @@ finalize_kernel(FinalizeArgs a) {
   if (threadIdx.x == 0) { int nv = 0; for (int u = 0; u < ncand; ++u) nv += ex_id[u] >= 0; s_nvalid = nv; }
   __syncthreads();
   for (int t = s_nvalid + threadIdx.x; t < a.k; t += blockDim.x) emit(t, -INFINITY, -1);
-  if (a.ex.n_peers > 0 && a.ex.signal) {
-    // Delivery signal of the fused exchange: once EVERY block of this (last) finalize launch has pushed its rows to
-    // the peers, tell each peer "rank r delivered exchange #seq".  Every thread fences its own peer stores at system
-    // scope, the block barrier orders them before thread 0's counter bump, and the last block releases the flags.
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0 && atomicAdd(a.ex.done, 1u) == gridDim.x - 1) {
-      *a.ex.done = 0;
-      const uint64_t seq = *a.ex.seq + 1;
-      __threadfence_system();
-      for (int r = 0; r < a.ex.n_peers; ++r) st_release_sys(a.ex.flag[r] + (seq & 1ull) * a.ex.flag_parity_stride, seq);
-    }
-  }
 }
 
 // Cross-shard merge of exact (fp64 score, id) lists: [n_shards, nq, k] -> [nq, k].
@@ -439,15 +431,15 @@ merge_topk_kernel(const double* __restrict__ in_s, const int64_t* __restrict__ i
   }
 }
 
-// Fused exchange, receiving side.  Every rank's finalize kernels have stored their (fp64 score, id) rows into
-// slot [parity][rank] of EVERY rank's buffer (plain peer stores over NVLink).  This kernel, next in the stream:
-//   1. block 0 publishes "rank r delivered exchange #seq" into every rank's flag array (release at system scope:
-//      the finalize kernels' stores happen-before it by stream order);
-//   2. every block waits until all `world` flags of this rank show seq (acquire), i.e. all slots are complete;
-//   3. block q merges query q's world x k candidates by (score desc, id asc);
-//   4. the last block to finish bumps the sequence word, so a replayed CUDA graph advances by itself.
-// Two parities: rank A can only write exchange s+2 after its own merge s+1, which waited for B's delivery s+1,
-// which B issued after finishing its merge s -- so a slot is never overwritten while someone still reads it.
+// Fused exchange, receiving side.  Every rank's finalize kernels store their (fp64 score, id) rows into slot
+// [parity][rank] of EVERY rank's buffer as tagged 8-byte words (see FinalizeArgs::ExchangeOut).  This kernel, next in
+// the stream, has block q poll query q's world x k entries until all four words of each carry this exchange's tag,
+// then merges them by (score desc, id asc); the last block to finish bumps the sequence word, so a replayed CUDA graph
+// advances by itself.  Two parities: rank A can only write exchange s+2 after its own merge s+1, which waited for B's
+// rows of s+1, which B produced after finishing its merge s -- so a slot is never overwritten while someone reads it.
+__device__ __forceinline__ uint64_t ld_relaxed_sys(const uint64_t* p) {
+  uint64_t v; asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
 
 __global__ void __launch_bounds__(256)
 exchange_merge_kernel(ExchangeParams p) {
@@ -456,28 +448,24 @@ exchange_merge_kernel(ExchangeParams p) {
   int64_t* id = reinterpret_cast<int64_t*>(sc + p.world * p.k);
   __shared__ int s_nvalid;
   const uint64_t seq = *p.seq + 1;
-  const size_t par = (seq & 1ull) * p.parity_stride;
+  const uint32_t tag = static_cast<uint32_t>(seq);
+  const uint64_t* base = p.slots + (seq & 1ull) * p.parity_stride;
   const int qi = blockIdx.x, n = p.world * p.k;
-  if (p.signal && blockIdx.x == 0 && threadIdx.x < p.world) {
-    __threadfence_system();
-    st_release_sys(p.peer_flags[threadIdx.x] + (seq & 1ull) * p.world + p.rank, seq);
-  }
-  if (threadIdx.x < p.world) {
-    const uint64_t* f = p.flags + (seq & 1ull) * p.world + threadIdx.x;
-    const long long t0 = clock64();
-    while (ld_acquire_sys(f) < seq) {
-      __nanosleep(40);
-      if (clock64() - t0 > 4000000000ll) { atomicExch(p.status, 1u + threadIdx.x); break; }   // ~2 s: a peer died
-    }
-  }
   if (threadIdx.x == 0) s_nvalid = 0;
-  __syncthreads();
-  const uint64_t* base = p.slots + par;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int sh = i / p.k, t = i % p.k;
-    const uint64_t* slot = base + static_cast<size_t>(sh) * p.slot_stride + static_cast<size_t>(qi) * p.k + t;
-    sc[i] = __longlong_as_double(static_cast<long long>(__ldcv(slot)));
-    id[i] = static_cast<int64_t>(__ldcv(slot + p.plane_stride));
+    const uint64_t* e = base + static_cast<size_t>(sh) * p.slot_stride + (static_cast<size_t>(qi) * p.k + t) * 4;
+    uint64_t w0, w1, w2, w3;
+    const long long t0 = clock64();
+    for (;;) {
+      w0 = ld_relaxed_sys(e); w1 = ld_relaxed_sys(e + 1); w2 = ld_relaxed_sys(e + 2); w3 = ld_relaxed_sys(e + 3);
+      if (static_cast<uint32_t>(w0 >> 32) == tag && static_cast<uint32_t>(w1 >> 32) == tag &&
+          static_cast<uint32_t>(w2 >> 32) == tag && static_cast<uint32_t>(w3 >> 32) == tag) break;
+      if (clock64() - t0 > 4000000000ll) { atomicExch(p.status, 1u + sh); w0 = w1 = 0; w2 = w3 = 0xFFFFFFFFull; break; }   // ~2 s: a peer died
+      __nanosleep(20);
+    }
+    sc[i] = __longlong_as_double(static_cast<long long>((w1 << 32) | (w0 & 0xFFFFFFFFull)));
+    id[i] = static_cast<int64_t>((w3 << 32) | (w2 & 0xFFFFFFFFull));
   }
   __syncthreads();
   int local_valid = 0;
@@ -684,6 +672,28 @@ cudaError_t launch_gather_rows(const void* rows, const float* inv, const int64_t
   const int64_t blocks = (n * 32 + 255) / 256;
   gather_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(static_cast<const uint8_t*>(rows), inv, ids, user, org, map, n,
                                                                   row_bytes, static_cast<uint8_t*>(o_rows), o_inv, o_ids, o_user, o_org);
+  return cudaGetLastError();
+}
+
+// Per-query tenant scopes on the tensor-core path: one bit per distinct scope of the batch (<= 32) and corpus row.
+// Same predicate as simt_scores_kernel: row_user == u OR (o >= 0 AND row_org == o)  (weaviate_client.py:244-249).
+__global__ void row_scope_mask_kernel(const int32_t* __restrict__ row_user, const int32_t* __restrict__ row_org,
+                                      const int32_t* __restrict__ scopes, int n_scopes, int64_t n, uint32_t* __restrict__ out) {
+  __shared__ int32_t su[32], so[32];
+  if (threadIdx.x < n_scopes) { su[threadIdx.x] = scopes[2 * threadIdx.x]; so[threadIdx.x] = scopes[2 * threadIdx.x + 1]; }
+  __syncthreads();
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t u = row_user[i], o = row_org[i];
+  uint32_t m = 0u;
+  for (int s = 0; s < n_scopes; ++s) m |= static_cast<uint32_t>((u == su[s]) || (so[s] >= 0 && o == so[s])) << s;
+  out[i] = m;
+}
+
+cudaError_t launch_row_scope_mask(const int32_t* row_user, const int32_t* row_org, const int32_t* scopes, int n_scopes, int64_t n,
+                                  uint32_t* out, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  row_scope_mask_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(row_user, row_org, scopes, n_scopes, n, out);
   return cudaGetLastError();
 }
 

@@ -69,7 +69,7 @@ constexpr uint32_t kSlot = kTcQRows * 8u;   // byte stride between list slots of
 
 struct SmemLayout {
   uint32_t stage_bytes, box_bytes, lcap, fifo_recs, qs_kb;
-  uint32_t off_qs, off_list, off_norm, off_fifo, off_tau, off_bar, total;
+  uint32_t off_qs, off_list, off_norm, off_mask, off_fifo, off_tau, off_bar, total;
 };
 __host__ __device__ inline SmemLayout make_layout(int cta_group, int epi_groups, int num_stages, int ksel, int dim) {
   SmemLayout L;
@@ -83,6 +83,7 @@ __host__ __device__ inline SmemLayout make_layout(int cta_group, int epi_groups,
   L.off_qs = o;     o += L.qs_kb * (kTcQRows * 128u);
   L.off_list = o;   o += static_cast<uint32_t>(epi_groups) * L.lcap * kSlot;
   L.off_norm = o;   o += static_cast<uint32_t>(epi_groups) * 4u * 2u * kTcTileN * 4u;
+  L.off_mask = o;   o += static_cast<uint32_t>(epi_groups) * 4u * 2u * kTcTileN * 4u;   // per-row tenant-scope bit masks (kMask launches)
   // deferred-candidate FIFO: per thread kTcFifoRecs records of four adjacent scores (16 B) + a row tag
   L.fifo_recs = (epi_groups == 1 && ksel <= kTcFifoMaxKsel) ? kTcFifoRecs : 0u;
   L.off_fifo = o;   o += L.fifo_recs * kTcQRows * (16u + 4u);
@@ -248,7 +249,12 @@ __device__ __forceinline__ float read_threshold(const unsigned long long* tq, ui
 constexpr uint32_t kDescHi = 0x40004040u;  // SBO = 1024 B, descriptor version 1, SWIZZLE_128B
 constexpr uint32_t kNaNBits = 0x7FC00000u;
 
-template <int kCtaGroup, int kEpiGroups>
+// kMask: the queries of the batch carry different tenant scopes (user_id == u OR org_id == o,
+// weaviate_client.py:244-249).  A pre-pass has written one 32-bit word per corpus row -- bit s set when scope s of the
+// batch may see the row -- and every query knows its scope's bit: scores of invisible rows become NaN before anything
+// else looks at them, exactly like tombstones.  (One scope for the whole batch needs none of this: it folds into the
+// inverse norms.)
+template <int kCtaGroup, int kEpiGroups, bool kMask>
 __global__ void __launch_bounds__(32 * (4 * kEpiGroups + 3), 1)
 simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   constexpr int kEpiWarps = 4 * kEpiGroups;
@@ -262,6 +268,7 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
 
   const SmemLayout L = make_layout(kCtaGroup, kEpiGroups, p.num_stages, p.ksel, p.dim);
   float* normbuf = reinterpret_cast<float*>(smem + L.off_norm);      // [4 warps][2][64]
+  uint32_t* maskbuf = reinterpret_cast<uint32_t*>(smem + L.off_mask);  // [4 warps][2][64]
   volatile float* tau_s = reinterpret_cast<volatile float*>(smem + L.off_tau);   // [128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);
   uint64_t* full_bar = bars;                              // [kTcMaxStages]
@@ -610,6 +617,9 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         }
       }
       float* mynorm = normbuf + (warp - kThrWarps) * 2 * kTcTileN;
+      uint32_t* mymask = maskbuf + (warp - kThrWarps) * 2 * kTcTileN;
+      uint32_t mybit = 0u;                                       // this query's tenant-scope bit
+      if constexpr (kMask) { if (qglob < p.nq) mybit = 1u << (p.q_scope[qglob] & 31); }
       const uint32_t list_a = smem_u32(smem + L.off_list) + (static_cast<uint32_t>(grp) * L.lcap * kTcQRows + r) * 8u;
       // deferred-candidate FIFO (see drain_fifo) whenever shared memory has room for it
       const bool use_fifo = L.fifo_recs > 0;
@@ -628,18 +638,25 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       long long t_boot = 0, t_loop_end = 0;
 
       // inverse norms: tile(0) into buffer 0, tile(1) in flight in registers
+      uint32_t mm0 = 0u, mm1 = 0u;                              // (masks of the tile in flight, beside its norms)
       auto load_norms = [&](int li2, float& a, float& b2) {
         a = __uint_as_float(kNaNBits); b2 = a;
+        mm0 = 0u; mm1 = 0u;
         const int it2 = grp + li2 * kEpiGroups;
         if (it2 < my_tiles) {
           const int64_t rbase = static_cast<int64_t>(tset + it2 * n_tsets) * kTcTileN;
           if (rbase + lane < p.n_rows) a = __ldg(p.inv_norm + rbase + lane);
           if (rbase + lane + 32 < p.n_rows) b2 = __ldg(p.inv_norm + rbase + lane + 32);
+          if constexpr (kMask) {
+            if (rbase + lane < p.n_rows) mm0 = __ldg(p.row_mask + rbase + lane);
+            if (rbase + lane + 32 < p.n_rows) mm1 = __ldg(p.row_mask + rbase + lane + 32);
+          }
         }
       };
       float nn0, nn1;
       load_norms(0, nn0, nn1);
       mynorm[lane] = nn0; mynorm[lane + 32] = nn1;
+      if constexpr (kMask) { mymask[lane] = mm0; mymask[lane + 32] = mm1; }
       load_norms(1, nn0, nn1);
       __syncwarp();
 
@@ -658,7 +675,11 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
           tmem_wait_ld();
           float m = -INFINITY;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(a16[j]) * mynorm[c * 16 + j]);
+          for (int j = 0; j < 16; ++j) {
+            float v = __uint_as_float(a16[j]) * mynorm[c * 16 + j];
+            if constexpr (kMask) { if (!(mymask[c * 16 + j] & mybit)) v = __uint_as_float(kNaNBits); }
+            m = fmaxf(m, v);
+          }
           top4_insert(st.top, m);       // (the main loop skips the tracker for this tile: it is counted here)
         }
         const float pv0 = top4_get(st.top, xm);
@@ -691,6 +712,7 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         if (!(p.dbg_flags & 32)) {
           float* nnext = mynorm + ((li + 1) & 1) * kTcTileN;
           nnext[lane] = nn0; nnext[lane + 32] = nn1;
+          if constexpr (kMask) { uint32_t* mnext = mymask + ((li + 1) & 1) * kTcTileN; mnext[lane] = mm0; mnext[lane + 32] = mm1; }
           load_norms(li + 2, nn0, nn1);
           __syncwarp();
         }
@@ -719,6 +741,19 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
 
         // Fast path: scale by 1/|c_j| in place (packed FMUL2) and keep one running max per 16
         // scores.  (NaN norm = tombstone / out of range: fmaxf drops it, `>=` rejects it.)
+        if constexpr (kMask) {   // rows this query's tenant scope may not see: NaN, like tombstones
+          const uint32_t* mb = mymask + (li & 1) * kTcTileN;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const uint4 mk = *reinterpret_cast<const uint4*>(mb + c * 16 + j4 * 4);
+              if (!(mk.x & mybit)) acc[c][j4 * 4 + 0] = kNaNBits;
+              if (!(mk.y & mybit)) acc[c][j4 * 4 + 1] = kNaNBits;
+              if (!(mk.z & mybit)) acc[c][j4 * 4 + 2] = kNaNBits;
+              if (!(mk.w & mybit)) acc[c][j4 * 4 + 3] = kNaNBits;
+            }
+        }
         float cmax[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -855,9 +890,9 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   if (warp == kProducerWarp) tmem_dealloc<kCtaGroup>(tmem_base, 512);
 }
 
-template <int kCtaGroup, int kEpiGroups>
+template <int kCtaGroup, int kEpiGroups, bool kMask>
 cudaError_t launch_variant(const cudaLaunchConfig_t& cfg, const CUtensorMap& tm, const TcParams& p, size_t smem) {
-  auto kern = simtopk_tc_kernel<kCtaGroup, kEpiGroups>;
+  auto kern = simtopk_tc_kernel<kCtaGroup, kEpiGroups, kMask>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
   return cudaLaunchKernelEx(&cfg, kern, tm, p);
@@ -890,8 +925,13 @@ cudaError_t tc_launch(int cta_group, int epi_groups, int grid, const void* tmap,
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const CUtensorMap& tm = *reinterpret_cast<const CUtensorMap*>(tmap);
-  if (cta_group == 2) return epi_groups == 2 ? launch_variant<2, 2>(cfg, tm, p, smem) : launch_variant<2, 1>(cfg, tm, p, smem);
-  return epi_groups == 2 ? launch_variant<1, 2>(cfg, tm, p, smem) : launch_variant<1, 1>(cfg, tm, p, smem);
+  const bool mask = p.row_mask != nullptr;
+  if (cta_group == 2) {
+    if (epi_groups == 2) return mask ? launch_variant<2, 2, true>(cfg, tm, p, smem) : launch_variant<2, 2, false>(cfg, tm, p, smem);
+    return mask ? launch_variant<2, 1, true>(cfg, tm, p, smem) : launch_variant<2, 1, false>(cfg, tm, p, smem);
+  }
+  if (epi_groups == 2) return mask ? launch_variant<1, 2, true>(cfg, tm, p, smem) : launch_variant<1, 2, false>(cfg, tm, p, smem);
+  return mask ? launch_variant<1, 1, true>(cfg, tm, p, smem) : launch_variant<1, 1, false>(cfg, tm, p, smem);
 }
 
 }  // namespace aur

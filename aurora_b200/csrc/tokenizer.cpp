@@ -100,6 +100,15 @@ inline void append_utf8(std::string& s, uint32_t cp) {
   }
 }
 
+struct AsciiClass {
+  uint8_t cls[128];
+  AsciiClass() {
+    for (uint32_t c = 0; c < 128; ++c)
+      cls[c] = in_ranges(kRemoved, c) ? 1 : in_ranges(kSpace, c) ? 2 : in_ranges(kPunct, c) ? 3 : 0;
+  }
+};
+const AsciiClass kAscii;
+
 }  // namespace
 
 struct aur_tokenizer {
@@ -149,6 +158,14 @@ struct aur_tokenizer {
     std::vector<uint32_t> folded;
     size_t i = 0;
     while (i < n && out.size() - 1 < body_max) {
+      if (s[i] < 0x80) {   // ASCII fast path: one table look-up per character (0 other, 1 removed, 2 space, 3 punctuation)
+        const unsigned char c = s[i++];
+        const uint8_t cls_ = kAscii.cls[c];
+        if (cls_ == 0) word.push_back(lower && c >= 'A' && c <= 'Z' ? c + 32u : c);
+        else if (cls_ == 2) flush();
+        else if (cls_ == 3) { flush(); word.push_back(c); flush(); }
+        continue;
+      }
       const uint32_t cp = next_cp(s, n, i);
       if (in_ranges(kRemoved, cp)) continue;
       if (in_ranges(kSpace, cp)) { flush(); continue; }

@@ -219,33 +219,39 @@ class TextEncoder:
         return out
 
     def encode_append(self, index, texts: Sequence[str], ids: np.ndarray, user_codes=None, org_codes=None) -> None:
+        """Tokenise once (one multi-threaded C call with the native tokenizer), then encoder forward + shard append per
+        workspace-sized batch; nothing runs per text in Python."""
         ids = np.ascontiguousarray(ids, dtype=np.int64)
         tok, cu = self._tokenize(texts, self.max_len)
-        long_ones = [int(i) for i in np.nonzero(np.diff(cu) >= self.max_len)[0] if len(self._windows(texts[int(i)])) > 1]
-        short = [i for i in range(len(texts)) if i not in set(long_ones)]
+        lens = np.diff(cu)
+        long_ones = [int(i) for i in np.nonzero(lens >= self.max_len)[0] if len(self._windows(texts[int(i)])) > 1]
         u = None if user_codes is None else np.ascontiguousarray(user_codes, dtype=np.int32)
         o = None if org_codes is None else np.ascontiguousarray(org_codes, dtype=np.int32)
-        if short:
-            if self._native and not long_ones:
-                self._append_texts_native(index, texts, ids, u, o)
+        keep = np.ones(len(texts), dtype=bool)
+        keep[long_ones] = False
+        sel = np.nonzero(keep)[0]
+        i = 0
+        while i < len(sel):
+            j, toks = i, 0
+            while j < len(sel) and j - i < self._enc.max_seqs and toks + lens[sel[j]] <= self._enc.max_tokens:
+                toks += int(lens[sel[j]]); j += 1
+            if j == i:
+                raise ValueError(f"text {sel[i]} tokenizes to {lens[sel[i]]} tokens: more than max_tokens={self._enc.max_tokens}")
+            part = sel[i:j]
+            if len(part) == part[-1] - part[0] + 1:            # contiguous run: slice the packed buffer
+                t = tok[cu[part[0]]:cu[part[-1] + 1]]
+                c = (cu[part[0]:part[-1] + 2] - cu[part[0]]).astype(np.int32)
             else:
-                seqs = [tok[cu[i]:cu[i + 1]] for i in short]
-                sel = np.asarray(short)
-                i = 0
-                while i < len(seqs):
-                    j, toks = i, 0
-                    while j < len(seqs) and j - i < self._enc.max_seqs and toks + len(seqs[j]) <= self._enc.max_tokens:
-                        toks += len(seqs[j]); j += 1
-                    if j == i:
-                        raise ValueError(f"text {short[i]} tokenizes to {len(seqs[i])} tokens: more than max_tokens={self._enc.max_tokens}")
-                    t, c = pack_sequences(seqs[i:j])
-                    self._enc.encode_append(index, t, c, ids[sel[i:j]], None if u is None else u[sel[i:j]], None if o is None else o[sel[i:j]])
-                    i = j
+                t, c = pack_sequences([tok[cu[x]:cu[x + 1]] for x in part])
+            self._enc.encode_append(index, t, c, ids[part], None if u is None else u[part], None if o is None else o[part])
+            i = j
         for i in long_ones:                                           # averaged windows: the vector is formed on the host
             v = self._encode_long(texts[i])[None, :]
             index.add(v, ids[i:i + 1], None if u is None else u[i:i + 1], None if o is None else o[i:i + 1])
 
     def _append_texts_native(self, index, texts, ids, u, o) -> None:
+        """The same ingest as ONE C call (aur_encode_text_append: tokenise + batches + append inside the library), for
+        callers that know their texts fit the position table (over-long texts would be truncated there)."""
         blob, offs = self._tok._pack(list(texts))
         N.check(self._enc._lib.aur_encode_text_append(self._enc._h, self._tok._h, index._h, blob, _ptr(offs), len(texts), self.max_len,
                                                       self._enc.max_tokens, self._enc.max_seqs, _ptr(ids), _ptr(u), _ptr(o), 0))

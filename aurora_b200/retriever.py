@@ -253,25 +253,28 @@ class KnowledgeBase:
 
     def query_batch(self, reqs: List[Tuple[Optional[str], str, int, Optional[float], Optional[str]]]) -> List[List[SimpleNamespace]]:
         """Several tenant-scoped searches at once: ``(user_id, query, limit, alpha, org_id)`` each.  All query texts go
-        through ONE encoder batch; the dense leg runs as one kernel launch per distinct tenant scope (a uniform scope
-        folds into the row scale, so the tensor-core kernel serves it); fusion / shaping per request as in ``query``."""
+        through ONE encoder batch; the dense leg is ONE kernel launch per result size (the tenant scopes of the batch ride
+        along as per-row bit masks on the tensor-core kernel); fusion / shaping per request as in ``query``."""
         need = [i for i, (u, q, lim, a, o) in enumerate(reqs) if lim > 0 and (u or o) and (a is None or a > 0.0)]
         vecs = self.encoder.encode([reqs[i][1] for i in need]) if need else None
         dense: Dict[int, List[Tuple[int, float]]] = {}
         with self._lock:
-            groups: Dict[Tuple[int, int, int], List[int]] = {}
+            groups: Dict[int, List[Tuple[int, int, int]]] = {}      # fetch size -> [(position, user code, org code)]
             for pos, i in enumerate(need):
                 u, _, lim, a, o = reqs[i]
                 hybrid = a is not None and a < 1.0
                 fetch = max(1, min(_MAX_FETCH, lim if not hybrid else _MAX_FETCH))
                 cu = self._code(self._user_code, u, False) if u else -2
                 co = self._code(self._org_code, o, False) if o else -1
-                groups.setdefault((cu, -1 if co == -2 else co, fetch), []).append(pos)
-            for (cu, co, fetch), members in groups.items():
-                q = vecs[members]
-                ids, scores = self.index.search(q, fetch, np.full(len(members), cu, np.int32), np.full(len(members), co, np.int32))
-                for row, pos in enumerate(members):
-                    dense[need[pos]] = [(int(r), float(s_)) for r, s_ in zip(ids[row], scores[row]) if r >= 0]
+                groups.setdefault(fetch, []).append((pos, cu, -1 if co == -2 else co))
+            for fetch, members in groups.items():
+                # one launch for the whole group: up to 32 distinct tenant scopes per batch ride on the tensor-core
+                # kernel as per-row bit masks (csrc/capi.cu search_host); the library falls back by itself beyond that
+                pos = [m[0] for m in members]
+                ids, scores = self.index.search(vecs[pos], fetch, np.array([m[1] for m in members], np.int32),
+                                                np.array([m[2] for m in members], np.int32))
+                for row, p_ in enumerate(pos):
+                    dense[need[p_]] = [(int(r), float(s_)) for r, s_ in zip(ids[row], scores[row]) if r >= 0]
         out = []
         for i, (u, q, lim, a, o) in enumerate(reqs):
             out.append(self.query(q, lim, user_id=u, org_id=o, alpha=a, scoped=True, _dense=dense.get(i)))

@@ -132,33 +132,59 @@ def chunk_plan(n_rows: int):
     return [(c, lo, min(CHUNK, n_rows - lo)) for c, lo in enumerate(range(0, n_rows, CHUNK))]
 
 
-def verify_against_oracle(dev, cfg, n_rows: int, q_dev, got_ids, got_sc, sample=None, extra_chunks=()):
-    """Streaming exact top-k over the regenerated corpus (all of it, on this rank's device -> host, chunk by chunk)
-    for all queries or a sample of them.  Returns the parity block; raises if ids differ or scores drift > 1e-3."""
+def oracle_topk_of_chunks(dev, cfg, chunks, q_dev, qsel, extra_chunks=()):
+    """Exact (ids, scores) top-k of the sampled queries over the given corpus chunks [(gchunk, first row, rows)] -- the
+    per-rank half of a distributed check (every rank scans its own shard on the host, rank 0 merges)."""
     import torch
 
     from oracle.streaming_topk import StreamingTopk
 
-    nq = q_dev.shape[0]
-    qsel = np.arange(nq) if sample is None or sample >= nq else np.linspace(0, nq - 1, sample).astype(np.int64)
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))   # (torchrun pins OMP to 1)
     Q = q_dev.float().cpu().numpy()[qsel]
     st = StreamingTopk(Q, cfg["k"])
-    t0 = time.perf_counter()
-    for gchunk, lo, m in chunk_plan(n_rows):
-        rows = gen_chunk(dev, cfg["seed"], gchunk, m, cfg["dim"]).float().cpu().numpy()
+    for gchunk, lo, m in chunks:
+        rows = gen_chunk(dev, cfg["seed"], gchunk, m, cfg["dim"]).cpu().float().numpy()
         st.add_chunk(rows, np.arange(lo, lo + m, dtype=np.int64))
     for rows, ids in extra_chunks:
         st.add_chunk(rows, ids)
     oi, osc = st.finish()
+    return oi, osc.astype(np.float64), st.rows
+
+
+def verify_distributed(dist, world, rank, dev, cfg, my_chunks, q_dev, got_ids, got_sc, sample, extra_chunks=()):
+    """Every rank computes the oracle's exact top-k over ITS shard (regenerated chunk by chunk, device -> host), the
+    per-shard lists are gathered and merged by (score desc, id asc) on rank 0 -- the oracle's global answer without one
+    process scanning 100M rows -- and compared with the engine's merged result."""
+    nq = q_dev.shape[0]
+    qsel = np.arange(nq) if sample is None or sample >= nq else np.linspace(0, nq - 1, sample).astype(np.int64)
+    t0 = time.perf_counter()
+    oi, osc, scanned = oracle_topk_of_chunks(dev, cfg, my_chunks, q_dev, qsel, extra_chunks)
+    parts = [None] * world
+    if world > 1:
+        dist.all_gather_object(parts, (oi, osc, scanned))
+    else:
+        parts = [(oi, osc, scanned)]
+    if rank != 0:
+        return None
+    k = cfg["k"]
+    ids = np.concatenate([p[0] for p in parts], axis=1)
+    sc = np.concatenate([p[1] for p in parts], axis=1)
+    m_ids = np.full((len(qsel), k), -1, np.int64)
+    m_sc = np.full((len(qsel), k), -np.inf, np.float32)
+    for i in range(len(qsel)):
+        valid = np.nonzero(ids[i] >= 0)[0]
+        order = valid[np.lexsort((ids[i, valid], -sc[i, valid]))][:k]
+        m_ids[i, :len(order)] = ids[i, order]
+        m_sc[i, :len(order)] = sc[i, order].astype(np.float32)
     gi, gs = got_ids[qsel], got_sc[qsel]
-    exact = bool(np.array_equal(gi, oi))
-    fin = np.isfinite(osc)
-    dmax = float(np.max(np.abs(gs[fin] - osc[fin]))) if fin.any() else 0.0
-    out = {"ids_exact": exact, "max_dscore": dmax, "queries_checked": int(len(qsel)), "rows_scanned": int(st.rows),
-           "checker": "oracle.streaming_topk.StreamingTopk (exact re-score = oracle.cosine_topk.exact_cosine)",
-           "seconds": round(time.perf_counter() - t0, 1)}
+    exact = bool(np.array_equal(gi, m_ids))
+    fin = np.isfinite(m_sc)
+    dmax = float(np.max(np.abs(gs[fin] - m_sc[fin]))) if fin.any() else 0.0
+    out = {"ids_exact": exact, "max_dscore": dmax, "queries_checked": int(len(qsel)), "rows_scanned": int(sum(p[2] for p in parts)),
+           "checker": "oracle.streaming_topk.StreamingTopk per shard on the host cores (exact re-score = oracle.cosine_topk.exact_cosine), "
+                      "per-shard lists merged by (score desc, id asc)", "seconds": round(time.perf_counter() - t0, 1)}
     if not exact or dmax > 1e-3:
-        out["id_mismatches"] = int((gi != oi).sum())
+        out["id_mismatches"] = int((gi != m_ids).sum())
         raise SystemExit("PARITY FAILURE: " + json.dumps(out))
     return out
 
@@ -376,9 +402,10 @@ def run_search(args, name: str):
     e2e = nq / (e2e_ms * 1e-3)
 
     parity = None
-    if rank == 0 and not args.no_parity:
-        parity = verify_against_oracle(dev, cfg, n_total, q_dev, got_ids, got_sc, sample=None if name == "cfg2" else 48)
-        if world == 1:      # the host-buffer call's answer too
+    if not args.no_parity:
+        my_chunks = [c for c in chunk_plan(n_total) if row_lo <= c[1] < row_hi]
+        parity = verify_distributed(dist, world, rank, dev, cfg, my_chunks, q_dev, got_ids, got_sc, sample=None if name == "cfg2" else 48)
+        if rank == 0 and world == 1:      # the host-buffer call's answer too
             if not (np.array_equal(h_id.numpy(), got_ids)):
                 raise SystemExit("PARITY FAILURE: aur_search (host buffers) and aur_search_dev disagree")
     if rank != 0:
@@ -389,8 +416,13 @@ def run_search(args, name: str):
         return
 
     hbm_peak, tf_peak, peak_src = _peaks()
-    passes = (nq + 255) // 256
-    nq_pass = min(nq, 256)
+    # queries per kernel launch: 256 per CTA pair, up to four pairs side by side on the same tiles ("query super-blocks"),
+    # fewer when ceil((k + 8) / tile sets) would exceed 4 (same rule as csrc/capi.cu search_enqueue)
+    n_super = 4
+    while n_super > 1 and -(-(k + 8) // (74 // n_super)) > 4:
+        n_super -= 1
+    nq_pass = min(nq, 256 * n_super)
+    passes = -(-nq // nq_pass)
     shard_bytes = n_local * dim * 2 + nq_pass * dim * 2 + nq_pass * k * 8            # per kernel launch (one 256-query pass)
     flops_pass = 2.0 * nq_pass * n_local * dim
     if name == "cfg2":
@@ -399,7 +431,7 @@ def run_search(args, name: str):
     else:   # nq >= 512: arithmetic intensity 1024 flop/B, the tensor pipe binds
         achieved = flops_pass / (kernel_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                "hbm_gbs_per_pass": shard_bytes / (kernel_ms * 1e-3) / 1e9}
+                "hbm_gbs_per_launch": shard_bytes / (kernel_ms * 1e-3) / 1e9, "queries_per_launch": nq_pass}
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(tpath) and world == 1 and name == "cfg2":
@@ -527,6 +559,7 @@ def run_cfg5(args):
     e1.record()
     _barrier(torch, dist, world)
     quiet_ms = _max_over_ranks(torch, dist, world, dev, e0.elapsed_time(e1) / args.steps)
+    st_quiet = ix.stats()                                      # kernel time of an undisturbed step (roofline)
 
     rows_before = ix.stats()["rows"]
     th = threading.Thread(target=ingest_loop)
@@ -560,20 +593,16 @@ def run_cfg5(args):
     torch.cuda.synchronize()
     parity = None
     if not args.no_parity:
-        # every rank contributes its appended tail (read back from its shard) to rank 0
-        tail_rows, tail_ids = ix.read_rows(per_gpu, st["rows"] - per_gpu)
-        gathered = [None] * world
-        if world > 1:
-            dist.all_gather_object(gathered, (tail_rows, tail_ids))
-        else:
-            gathered = [(tail_rows, tail_ids)]
-        if rank == 0:
-            from oracle import cosine_topk as O
+        # every rank checks its own shard (base chunks + the tail its ingest thread appended, read back from HBM)
+        from oracle import cosine_topk as O
 
-            extra = [(O.bf16_bits_to_f32(r), i) for r, i in gathered if len(i)]
-            parity = verify_against_oracle(dev, cfg, n_total, q_dev, out_i.cpu().numpy(), out_s.cpu().numpy(), sample=24,
-                                           extra_chunks=extra)
-            parity["appended_rows_included"] = int(sum(len(i) for _, i in gathered))
+        tail_rows, tail_ids = ix.read_rows(per_gpu, st["rows"] - per_gpu)
+        extra = [(O.bf16_bits_to_f32(tail_rows), tail_ids)] if len(tail_ids) else []
+        my_chunks = [(rank * chunks_per_gpu + c, (rank * chunks_per_gpu + c) * CHUNK, CHUNK) for c in range(chunks_per_gpu)]
+        parity = verify_distributed(dist, world, rank, dev, cfg, my_chunks, q_dev, out_i.cpu().numpy(), out_s.cpu().numpy(), sample=16,
+                                    extra_chunks=extra)
+        if parity is not None:
+            parity["appended_rows_rank0"] = int(len(tail_ids))
     if rank != 0:
         sh.close()
         if world > 1:
@@ -581,9 +610,9 @@ def run_cfg5(args):
             dist.destroy_process_group()
         return
     hbm_peak, tf_peak, peak_src = _peaks()
-    n_local = st["rows"]
-    flops_pass = 2.0 * 256 * n_local * dim
-    kernel_ms = st["last_kernel_ms"]
+    n_local = st_quiet["rows"]
+    flops_pass = 2.0 * nq * n_local * dim                      # one launch: 512 queries = two CTA-pair super-blocks
+    kernel_ms = st_quiet["last_kernel_ms"]
     out = {
         "metric": cfg["metric"], "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -600,8 +629,8 @@ def run_cfg5(args):
         "gpu_launches": st["last_launches"] * args.steps,
         "parity": parity,
         "roofline": {"bound": "tensor", "achieved": flops_pass / (kernel_ms * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
-                     "frac": flops_pass / (kernel_ms * 1e-3) / 1e12 / tf_peak, "kernel": "simtopk_tc_kernel (quiescent, one 256-query pass)",
-                     "kernel_ms": kernel_ms, "hbm_gbs_per_pass": n_local * dim * 2 / (kernel_ms * 1e-3) / 1e9, "peak_source": peak_src, "traffic": None},
+                     "frac": flops_pass / (kernel_ms * 1e-3) / 1e12 / tf_peak, "kernel": "simtopk_tc_kernel (no ingest running, one launch = all 512 queries)",
+                     "kernel_ms": kernel_ms, "hbm_gbs_per_launch": n_local * dim * 2 / (kernel_ms * 1e-3) / 1e9, "peak_source": peak_src, "traffic": None},
         "clocks": clk.summary(),
     }
     sh.close()
@@ -674,6 +703,7 @@ def run_cfg3(args):
     ms_wall = _max_over_ranks(torch, dist, world, dev, wall_ms)
     st = enc.stats()
     flops = st["gemm_flops"] + st["attn_flops"]
+    from_text = text_ingest_leg(torch, dist, world, rank, dev, enc, ix, cfg, n_seq, lens, nxt)
     # parity: the vectors that landed in the shard vs the numpy BERT oracle on two chunks
     parity = None
     if rank == 0 and not args.no_parity:
@@ -712,6 +742,7 @@ def run_cfg3(args):
                 "h2d_bytes_per_step": int(tok.nbytes + cu.nbytes + n_seq * 16), "d2h_bytes_per_step": 0,
                 "note": "wall clock of aur_encode_append from host token ids (H2D inside), vectors stay in HBM (shard append)"},
         "gpu_launches": int(st["launches"] + 2) * args.steps,
+        "from_text": from_text,
         "parity": parity,
         "roofline": {"bound": "tensor", "achieved": flops / (ms_dev * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
                      "frac": flops / (ms_dev * 1e-3) / 1e12 / tf_peak, "peak_source": peak_src, "traffic": None,
@@ -721,6 +752,76 @@ def run_cfg3(args):
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
+
+
+def synth_vocab_and_texts(vocab_size: int, lens, seed: int):
+    """A synthetic uncased vocabulary of `vocab_size` pieces (no vocab.txt ships offline) and one text per target token
+    count: words drawn from the vocabulary, every ~9th word a two-piece word, some punctuation -- runbook-like."""
+    rng = np.random.default_rng(seed)
+    letters = np.array(list("abcdefghijklmnopqrstuvwxyz"))
+    words = set()
+    while len(words) < (vocab_size - 5) * 3 // 4:
+        words.add("".join(rng.choice(letters, size=int(rng.integers(2, 9)))))
+    words = sorted(words)
+    tails = set()
+    while len(tails) < vocab_size - 5 - len(words):
+        tails.add("##" + "".join(rng.choice(letters, size=int(rng.integers(1, 5)))))
+    pieces = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"] + words + sorted(tails)
+    tails = sorted(tails)
+    texts = []
+    for n in lens:
+        out, toks = [], 2
+        while toks < n:
+            w = words[int(rng.integers(len(words)))]
+            if rng.random() < 0.11 and toks + 2 <= n:
+                w += tails[int(rng.integers(len(tails)))][2:]; toks += 1      # (may tokenise differently; lengths are approximate)
+            out.append(w); toks += 1
+            if rng.random() < 0.08 and toks < n:
+                out.append(","); toks += 1
+        texts.append(" ".join(out))
+    return pieces, texts
+
+
+def text_ingest_leg(torch, dist, world, rank, dev, enc, ix, cfg, n_seq, lens, nxt) -> dict:
+    """cfg3 FROM TEXT: the same batch shape as raw text -> C++ WordPiece (all host cores) -> encoder -> shard, one
+    aur_encode_text_append call per batch; and the tokenizer alone (host-side chunks/s)."""
+    from aurora_b200.encoder import TextEncoder
+    from aurora_b200.wordpiece import NativeTokenizer
+
+    pieces, texts = synth_vocab_and_texts(cfg.vocab, lens, 4242 + rank)
+    tok = NativeTokenizer(pieces)
+    te = TextEncoder(enc, tok)
+    tk, cu_t = tok.encode_packed(texts, 512)
+    big = texts * 8                                            # 1536 chunks: enough work for all cores
+    tok.encode_packed(big, 512)
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        tok.encode_packed(big, 512)
+    tok_rate = reps * len(big) / (time.perf_counter() - t0)
+    t1 = time.perf_counter()
+    tok.encode_packed(big, 512, threads=1)
+    tok_rate_1 = len(big) / (time.perf_counter() - t1)
+
+    def step():
+        ids = (rank << 40) + np.arange(nxt[0], nxt[0] + n_seq, dtype=np.int64)
+        nxt[0] += n_seq
+        te.encode_append(ix, texts, ids)
+
+    for _ in range(2):
+        step()
+    _barrier(torch, dist, world)
+    t0 = time.perf_counter()
+    k = 5
+    for _ in range(k):
+        step()
+    torch.cuda.synchronize()
+    ms = _max_over_ranks(torch, dist, world, dev, (time.perf_counter() - t0) * 1e3 / k)
+    return {"chunks_per_s": world * n_seq / (ms * 1e-3), "ms_per_batch": ms, "tokens_per_batch": int(cu_t[-1]),
+            "call": "aur_encode_text_append (C++ WordPiece on the host cores -> encoder forward -> shard append), text bytes in",
+            "tokenizer_only_chunks_per_s": tok_rate, "tokenizer_only_chunks_per_s_1_thread": tok_rate_1,
+            "host_cores": os.cpu_count() or 1, "vocab": "synthetic 30522-piece uncased vocabulary (no vocab.txt offline)",
+            "text_bytes_per_batch": int(sum(len(t) for t in texts))}
 
 
 def encoder_leg(device: int) -> dict:

@@ -179,7 +179,8 @@ int aur_merge_topk_packed_dev(int32_t device, const void* packed, int32_t n_shar
 
 /* Fused exchange ("fused variant"): instead of a local top-k array + ncclAllGather + merge, the
  * kernel that produces a shard's exact top-k stores it straight into EVERY rank's exchange buffer over NVLink
- * (peer-mapped through CUDA IPC), and the merge kernel that follows waits on per-rank delivery flags.  One
+ * (peer-mapped through CUDA IPC) as 8-byte words that each carry 4 bytes of payload and a 4-byte sequence tag, and the
+ * merge kernel that follows polls those words until the tags match -- no flag, fence or collective on the path.  One
  * process per GPU:
  *   1. every rank:  aur_exchange_create(...)      -> its 64-byte IPC handle
  *   2. all-gather the handles (any host transport: torch.distributed, MPI, a file)

@@ -94,7 +94,8 @@ def test_simt_tenant_filter_and_tombstones():
 def test_uniform_tenant_scope_is_served_by_the_tcgen05_kernel(with_org):
     """The reference asks one tenant's question at a time (user_id == u OR org_id == o,
     weaviate_client.py:244-249): with one scope for the whole batch the filter folds into the row scale
-    and the tensor-core kernel serves it; mixed scopes in one batch stay on the generic kernel."""
+    and the tensor-core kernel serves it; a batch mixing up to 32 scopes (the daemon's coalesced requests) rides on the
+    same kernel through per-row bit masks; beyond that the generic kernel takes over."""
     n, d, nq, k = 30000, 768, 70, 16
     C, Q = _data(n, d, nq, seed=99)
     rng = np.random.default_rng(5)
@@ -112,10 +113,19 @@ def test_uniform_tenant_scope_is_served_by_the_tcgen05_kernel(with_org):
         _check(ids, sc, *O.cosine_topk(Q, C, k, live=live, row_user=ru, row_org=ro, q_user=qu, q_org=qo))
         vis = (ru[ids[ids >= 0]] == 7) | ((qo[0] >= 0) & (ro[ids[ids >= 0]] == qo[0]))
         assert vis.all()
-        qu2 = qu.copy(); qu2[1] = 8                                    # two different scopes in one batch
+        qu2 = qu.copy(); qu2[1] = 8                                    # two different scopes in one batch: row bit masks
         ids2, sc2 = ix.search(Q, k, qu2, qo)
-        assert ix.stats()["last_kernel"] == N.KERNEL_SIMT
+        assert ix.stats()["last_kernel"] == N.KERNEL_TC2
         _check(ids2, sc2, *O.cosine_topk(Q, C, k, live=live, row_user=ru, row_org=ro, q_user=qu2, q_org=qo))
+        rng2 = np.random.default_rng(77)                               # a coalesced batch: 20 tenants' questions at once
+        qu3 = rng2.integers(0, 20, nq).astype(np.int32); qo3 = rng2.integers(-1, 6, nq).astype(np.int32)
+        ids3, sc3 = ix.search(Q, k, qu3, qo3)
+        assert ix.stats()["last_kernel"] == N.KERNEL_TC2
+        _check(ids3, sc3, *O.cosine_topk(Q, C, k, live=live, row_user=ru, row_org=ro, q_user=qu3, q_org=qo3))
+        qu4 = np.arange(nq, dtype=np.int32) % 40                       # more than 32 distinct scopes: generic kernel
+        ids4, sc4 = ix.search(Q, k, qu4, np.full(nq, -1, np.int32))
+        assert ix.stats()["last_kernel"] == N.KERNEL_SIMT
+        _check(ids4, sc4, *O.cosine_topk(Q, C, k, live=live, row_user=ru, row_org=ro, q_user=qu4, q_org=np.full(nq, -1, np.int32)))
         none = ix.search(Q, k, np.full(nq, 1234, np.int32), np.full(nq, -1, np.int32))   # a tenant with no rows
         assert (none[0] == -1).all()
 
@@ -127,9 +137,6 @@ def test_uniform_tenant_scope_is_served_by_the_tcgen05_kernel(with_org):
     (777, 64, 1, 1), (12345, 256, 129, 128), (64, 768, 256, 32), (5000, 768, 128, 64),
     # dims past 768: the first 768 dims of the queries sit in TMEM, the rest in shared memory (SS MMAs)
     (20000, 1024, 256, 32), (9000, 1024, 300, 64), (7000, 896, 130, 10), (4000, 832, 64, 5),
-    # more than 256 queries per launch: several CTA pairs ("query super-blocks") walk the same tiles side by side, fewer
-    # tile sets, so every CTA vouches for 2-4 rows in the threshold exchange
-    (40000, 768, 1024, 32), (30000, 768, 600, 10), (25000, 1024, 1024, 100), (60000, 768, 512, 32), (3000, 768, 900, 64),
 ])
 def test_tcgen05_parity(kernel, n, d, nq, k):
     C, Q = _data(n, d, nq, seed=n % 1000 + nq + d)
@@ -138,6 +145,23 @@ def test_tcgen05_parity(kernel, n, d, nq, k):
         ix.set_kernel(kernel)
         ids, sc = ix.search(Q, k)
         assert ix.stats()["last_kernel"] == kernel
+    _check(ids, sc, *O.cosine_topk(Q, C, k))
+
+
+@pytest.mark.parametrize("n,d,nq,k", [
+    (40000, 768, 1024, 32), (30000, 768, 600, 10), (25000, 1024, 1024, 100), (60000, 768, 512, 32), (3000, 768, 900, 64),
+    (20000, 768, 257, 128), (9000, 512, 1024, 5), (70000, 768, 2100, 16),
+])
+def test_query_super_blocks(n, d, nq, k):
+    """More than 256 queries per launch: up to four CTA pairs ("query super-blocks") walk the same corpus tiles side by
+    side (the corpus crosses HBM once per 256 x S queries, the siblings hit L2).  Fewer tile sets scan the corpus then, so
+    every CTA vouches for 2-4 rows in the threshold exchange (best four chunk maxima); batches past 1024 queries and
+    large k (fewer super-blocks per launch) split into several launches."""
+    C, Q = _data(n, d, nq, seed=n % 977 + nq + k, planted=3)
+    with Index(d, n) as ix:
+        ix.add(C, np.arange(n, dtype=np.int64))
+        ids, sc = ix.search(Q, k)
+        assert ix.stats()["last_kernel"] == N.KERNEL_TC2
     _check(ids, sc, *O.cosine_topk(Q, C, k))
 
 

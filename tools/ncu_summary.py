@@ -1,21 +1,26 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep here (no GPU): headline metrics + hottest SASS lines with stall reasons.
-usage: python tools/ncu_summary.py <report.ncu-rep> [n_top]"""
+usage: python tools/ncu_summary.py <report.ncu-rep> [n_top] [kernel-name regex]"""
 import csv, io, subprocess, sys
 
+KSEL = []
+
 def raw(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"] + KSEL, capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units, vals = rows[0], rows[1], rows[2]
     return {h: (u, v) for h, u, v in zip(hdr, units, vals)}
 
 def source(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + KSEL, capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    return rows[0], rows[1], rows[2:]
+    hi = [i for i, r in enumerate(rows) if "Address" in r][0]
+    return rows[0], rows[hi], rows[hi + 1:]
 
 def main():
     rep = sys.argv[1]; ntop = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+    if len(sys.argv) > 3:
+        KSEL.extend(["--kernel-name", "regex:" + sys.argv[3]])
     m = raw(rep)
     keys = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
             "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum.per_second",

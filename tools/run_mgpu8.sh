@@ -1,0 +1,17 @@
+set -x
+N=8
+T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
+O=gpurun_out/bench_r2_n$N
+nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw --format=csv | head -9
+timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > gpurun_out/mgpu_test_n$N.log 2>&1; rc=$?; tail -5 gpurun_out/mgpu_test_n$N.log
+if [ $rc -ne 0 ]; then echo "MULTI-GPU PARITY TEST FAILED: skipping the benches"; tail -40 gpurun_out/mgpu_test_n$N.log; exit 1; fi
+for n in 8 4 2; do
+  TT="python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511"
+  timeout 200 $TT bench.py --gpus $n --steps 50 --warmup 5 --exchange fused --graph > gpurun_out/bench_r2_n${n}_fused_graph.json 2> gpurun_out/bench_r2_n${n}_fused_graph.err; tail -c 200 gpurun_out/bench_r2_n${n}_fused_graph.json; tail -2 gpurun_out/bench_r2_n${n}_fused_graph.err
+done
+python bench.py --gpus 1 --steps 50 --warmup 5 --graph --no-encoder > gpurun_out/bench_r2_n1_graph.json 2> gpurun_out/bench_r2_n1_graph.err; tail -c 200 gpurun_out/bench_r2_n1_graph.json
+timeout 200 $T bench.py --gpus $N --steps 50 --warmup 5 --exchange fused > ${O}_fused.json 2> ${O}_fused.err; tail -c 200 ${O}_fused.json; tail -2 ${O}_fused.err
+timeout 200 $T bench.py --gpus $N --steps 50 --warmup 5 --exchange nccl > ${O}_nccl.json 2> ${O}_nccl.err; tail -c 200 ${O}_nccl.json; tail -2 ${O}_nccl.err
+timeout 300 $T bench.py --gpus $N --steps 20 --warmup 3 --config cfg4 --graph > ${O}_cfg4.json 2> ${O}_cfg4.err; tail -c 200 ${O}_cfg4.json; tail -2 ${O}_cfg4.err
+timeout 300 $T bench.py --gpus $N --steps 10 --warmup 3 --config cfg3 > ${O}_cfg3.json 2> ${O}_cfg3.err; tail -c 200 ${O}_cfg3.json; tail -2 ${O}_cfg3.err
+AUR_BENCH_ROWS=12500000 timeout 700 $T bench.py --gpus $N --steps 20 --warmup 3 --config cfg5 > ${O}_cfg5.json 2> ${O}_cfg5.err; tail -c 200 ${O}_cfg5.json; tail -2 ${O}_cfg5.err
