@@ -62,24 +62,28 @@ class BM25Index:
                     del self._postings[t]
         return True
 
-    def search(self, query: str, limit: int, allow: Optional[Callable[[int], bool]] = None) -> List[Tuple[int, float]]:
-        """Top-``limit`` (doc id, BM25 score), best first; ties by ascending id.  ``allow`` is the
-        pre-filter (tenant scope): documents it rejects do not exist for this query."""
+    def search(self, query: str, limit: int, allow: Optional[Callable[[int], bool]] = None,
+               allowed: Optional[set] = None) -> List[Tuple[int, float]]:
+        """Top-``limit`` (doc id, BM25 score), best first; ties by ascending id.  The pre-filter (tenant scope,
+        metadata filter) comes as ``allowed`` -- a set of visible doc ids, intersected with every posting list at C
+        speed -- or as a predicate ``allow``: documents outside do not exist for this query."""
         n_docs = len(self._doc_len)
         if n_docs == 0 or limit <= 0:
             return []
         avgdl = self._total_len / n_docs if self._total_len else 1.0
         scores: Dict[int, float] = defaultdict(float)
+        doc_len = self._doc_len
         for term in set(tokenize(query)):
             plist = self._postings.get(term)
             if not plist:
                 continue
             idf = math.log(1.0 + (n_docs - len(plist) + 0.5) / (len(plist) + 0.5))
-            for doc, tf in plist.items():
+            docs = plist.keys() & allowed if allowed is not None else plist.keys()
+            for doc in docs:
                 if allow is not None and not allow(doc):
                     continue
-                dl = self._doc_len[doc]
-                scores[doc] += idf * tf * (K1 + 1.0) / (tf + K1 * (1.0 - B + B * dl / avgdl))
+                tf = plist[doc]
+                scores[doc] += idf * tf * (K1 + 1.0) / (tf + K1 * (1.0 - B + B * doc_len[doc] / avgdl))
         return sorted(scores.items(), key=lambda kv: (-kv[1], kv[0]))[:limit]
 
 

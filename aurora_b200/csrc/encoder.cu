@@ -169,7 +169,7 @@ int forward_locked(aur_encoder* e, const int32_t* cu_host, int n_seq, int n_item
     Layer& L = e->layers[l];
     int rc;
     if ((rc = gemm(e, &e->tm_x, &L.tm_wqkv, &e->tmo_qkv, T, 3 * HP, H, kEpiBias, L.bqkv, nullptr, 0))) return rc;
-    ENC_TRY(attn_tc_launch(e->sm_count, &e->tm_qkv, ap, s));
+    ENC_TRY(attn_launch(e->sm_count, &e->tm_qkv, ap, s));
     if ((rc = gemm(e, &e->tm_ctx, &L.tm_wo, &e->tmo_y, T, H, HP, kEpiBiasResid, L.bo, e->x, H))) return rc;
     ENC_TRY(launch_layernorm(e->y, L.ln1_g, L.ln1_b, c.ln_eps, T, H, e->x, s));
     if ((rc = gemm(e, &e->tm_x, &L.tm_wi, &e->tmo_inter, T, I, H, kEpiBiasGelu, L.bi, nullptr, 0))) return rc;
@@ -480,7 +480,7 @@ int aur_debug_attention(int32_t device, const uint16_t* qkv, const int32_t* cu, 
   cudaError_t ce = cudaSuccess;
   for (int rep = 0; rep < 3 && ce == cudaSuccess; ++rep) {
     cudaEventRecord(e0, nullptr);
-    ce = attn_tc_launch(prop.multiProcessorCount, &tm, ap, nullptr);
+    ce = attn_launch(prop.multiProcessorCount, &tm, ap, nullptr);
     cudaEventRecord(e1, nullptr);
   }
   if (ce == cudaSuccess) ce = cudaDeviceSynchronize();

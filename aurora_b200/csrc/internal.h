@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace aur {
 
@@ -180,6 +181,13 @@ struct AttnParams {
 };
 // tmap_qkv: CUtensorMap over the packed [tokens, 3*hidden] projections, box {64, 128}, SWIZZLE_128B.
 cudaError_t attn_tc_launch(int sm_count, const void* tmap_qkv, const AttnParams& p, cudaStream_t s);
+// Version 2 (attn_tc2.cu): two work items in flight per CTA, one key block at a time, online softmax.  Same arguments.
+cudaError_t attn_tc2_launch(int sm_count, const void* tmap_qkv, const AttnParams& p, cudaStream_t s);
+// The attention kernel the encoder uses: version 2 unless AUR_ATTN_V1=1 is set in the environment (A/B runs).
+inline cudaError_t attn_launch(int sm_count, const void* tmap_qkv, const AttnParams& p, cudaStream_t s) {
+  static const bool v1 = [] { const char* e = getenv("AUR_ATTN_V1"); return e && e[0] == '1'; }();
+  return v1 ? attn_tc_launch(sm_count, tmap_qkv, p, s) : attn_tc2_launch(sm_count, tmap_qkv, p, s);
+}
 
 cudaError_t launch_embed_ln(const int32_t* tok, const int32_t* pos, int n_tok, int n_rows_pad,
                             const __nv_bfloat16* word, const __nv_bfloat16* pos_emb, const __nv_bfloat16* type_emb,

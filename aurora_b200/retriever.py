@@ -231,15 +231,15 @@ class KnowledgeBase:
             if not hybrid:
                 picked = [(rid, sc, sc) for rid, sc in dense[:limit]]
             else:
-                allowed_set = None if allowed is None else set(allowed)
-
-                def allow(doc: int) -> bool:
-                    if allowed_set is not None:
-                        return doc in allowed_set
-                    props = self._props.get(doc)
-                    return props is not None and tenant_ok(props)
-
-                sparse = self.sparse.search(query, _MAX_FETCH, allow)
+                # keyword leg under the same pre-filter: the resolved filter's ids, else the tenant's own inverted lists
+                if allowed is not None:
+                    allowed_set = set(allowed)
+                elif tenant:
+                    allowed_set = (self._by_user.get(user_id, set()) if user_id else set()) | \
+                                  (self._by_org.get(org_id, set()) if org_id else set())
+                else:
+                    allowed_set = None
+                sparse = self.sparse.search(query, _MAX_FETCH, allowed=allowed_set)
                 from .bm25 import ranked_fusion
 
                 cos = dict(dense)

@@ -84,8 +84,13 @@ def test_simt_tenant_filter_and_tombstones():
         assert ix.remove(dead) == 500
         assert ix.remove(dead[:10]) == 0
         live[dead] = False
-        ids, sc = ix.search(Q, k, qu, qo)                       # filtered => generic path
+        ix.set_kernel(N.KERNEL_SIMT)                            # the generic kernel's own per-query filter
+        ids, sc = ix.search(Q, k, qu, qo)
         st = ix.stats()
+        ix.set_kernel(N.KERNEL_AUTO)                            # same batch in AUTO: <= 32 scopes -> tensor path, row bit masks
+        ids_tc, sc_tc = ix.search(Q, k, qu, qo)
+        assert ix.stats()["last_kernel"] == N.KERNEL_TC2
+        assert np.array_equal(ids_tc, ids) and np.array_equal(sc_tc, sc)
     assert st["last_kernel"] == N.KERNEL_SIMT and st["live"] == n - 500 and st["rows"] == n
     _check(ids, sc, *O.cosine_topk(Q, C, k, live=live, row_user=ru, row_org=ro, q_user=qu, q_org=qo))
 
@@ -118,7 +123,7 @@ def test_uniform_tenant_scope_is_served_by_the_tcgen05_kernel(with_org):
         assert ix.stats()["last_kernel"] == N.KERNEL_TC2
         _check(ids2, sc2, *O.cosine_topk(Q, C, k, live=live, row_user=ru, row_org=ro, q_user=qu2, q_org=qo))
         rng2 = np.random.default_rng(77)                               # a coalesced batch: 20 tenants' questions at once
-        qu3 = rng2.integers(0, 20, nq).astype(np.int32); qo3 = rng2.integers(-1, 6, nq).astype(np.int32)
+        qu3 = rng2.integers(0, 20, nq).astype(np.int32); qo3 = (qu3 % 7 - 1).astype(np.int32)   # 20 distinct (user, org) scopes
         ids3, sc3 = ix.search(Q, k, qu3, qo3)
         assert ix.stats()["last_kernel"] == N.KERNEL_TC2
         _check(ids3, sc3, *O.cosine_topk(Q, C, k, live=live, row_user=ru, row_org=ro, q_user=qu3, q_org=qo3))

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import json
 import os
+import subprocess
 import sys
 import tempfile
 import threading
@@ -20,15 +21,40 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-import bench  # noqa: E402
-from aurora_b200 import retriever as R  # noqa: E402
 from aurora_b200.daemon import Client, serve  # noqa: E402
-from aurora_b200.encoder import Encoder, EncoderConfig, TextEncoder  # noqa: E402
-from aurora_b200.wordpiece import NativeTokenizer  # noqa: E402
+
+
+def client_main(argv):
+    """One client process: `threads` threads, `per_thread` single-query calls each (no GPU, no engine import)."""
+    path, threads, per_thread, n_tenants, pid, out, qfile = argv[0], int(argv[1]), int(argv[2]), int(argv[3]), int(argv[4]), argv[5], argv[6]
+    queries = json.load(open(qfile))
+    lat, errs = [], []
+
+    def worker(i):
+        try:
+            c = Client(path)
+            for j in range(per_thread):
+                t1 = time.time()
+                r = c.search_knowledge_base(f"user{(pid * 7 + i + j) % n_tenants}", queries[(pid * 131 + i * 31 + j) % len(queries)], limit=5)
+                lat.append(time.time() - t1)
+                assert isinstance(r, list) and len(r) == 5, r
+        except Exception as e:      # pragma: no cover
+            errs.append(repr(e))
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(threads)]
+    t0 = time.time()
+    [t.start() for t in ts]; [t.join() for t in ts]
+    json.dump({"lat": lat, "t0": t0, "t1": time.time(), "errs": errs}, open(out, "w"))
+    sys.exit(1 if errs else 0)
 
 
 def main():
     out = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/daemon_load.json"
+    import bench
+    from aurora_b200 import retriever as R
+    from aurora_b200.encoder import Encoder, EncoderConfig, TextEncoder
+    from aurora_b200.wordpiece import NativeTokenizer
+
     cfg = EncoderConfig()
     rng = np.random.default_rng(5)
     lens = np.clip(np.rint(rng.normal(200, 60, 96)), 16, 400).astype(np.int64)
@@ -49,28 +75,30 @@ def main():
     queries = [" ".join(texts[i % len(texts)].split()[:24]) for i in range(256)]
     res = {"chunks_ingested": n_chunks, "ingest_chunks_per_s": n_chunks / ingest_s, "tenants": n_tenants}
     with tempfile.TemporaryDirectory() as tmp:
-        for label, coalesce_us, n_threads, per_thread in (("single_caller", 0, 1, 200), ("64_callers_no_coalescing", 0, 64, 40),
-                                                          ("64_callers_coalesced", 300, 64, 40)):
+        qfile = os.path.join(tmp, "queries.json")
+        json.dump(queries, open(qfile, "w"))
+        for label, coalesce_us, n_threads, per_thread in (("single_caller", 0, 1, 300), ("64_callers_no_coalescing", 0, 64, 60),
+                                                          ("64_callers_coalesced", 300, 64, 60)):
             path = os.path.join(tmp, f"{label}.sock")
             srv = serve(path, background=True, coalesce_us=coalesce_us)
-            errs, lat = [], []
-
-            def worker(i):
-                try:
-                    c = Client(path)
-                    for j in range(per_thread):
-                        t1 = time.perf_counter()
-                        r = c.search_knowledge_base(f"user{(i + j) % n_tenants}", queries[(i * 31 + j) % len(queries)], limit=5)
-                        lat.append(time.perf_counter() - t1)
-                        assert isinstance(r, list) and len(r) == 5, r
-                except Exception as e:      # pragma: no cover
-                    errs.append(repr(e))
-
             Client(path).search_knowledge_base("user0", queries[0], limit=5)      # warm
-            ts = [threading.Thread(target=worker, args=(i,)) for i in range(n_threads)]
+            # clients are separate PROCESSES, like gunicorn workers / Celery children in the reference: the daemon's
+            # interpreter is not shared with them
+            n_procs = min(n_threads, 8)
+            per_proc = n_threads // n_procs
+            outs = [os.path.join(tmp, f"{label}.{i}.json") for i in range(n_procs)]
             t0 = time.perf_counter()
-            [t.start() for t in ts]; [t.join() for t in ts]
+            procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--client", path, str(per_proc), str(per_thread),
+                                       str(n_tenants), str(i), outs[i], qfile]) for i in range(n_procs)]
+            rcs = [pr.wait() for pr in procs]
             wall = time.perf_counter() - t0
+            errs = [f"client process {i} exited {rc}" for i, rc in enumerate(rcs) if rc != 0]
+            lat, spans = [], []
+            for o in outs:
+                if os.path.exists(o):
+                    d = json.load(open(o)); lat += d["lat"]; spans.append((d["t0"], d["t1"]))
+            if spans:
+                wall = max(b for _, b in spans) - min(a for a, _ in spans)      # first request sent .. last answer received
             h = Client(path).health()
             srv.shutdown(); srv.close_all(final_save=False); srv.server_close()
             if errs:
@@ -90,4 +118,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "--client":
+        client_main(sys.argv[2:])
+    else:
+        main()

@@ -17,8 +17,10 @@ with Index(d, n) as ix:
                rng.integers(0, 10, m).astype(np.int32), np.full(m, -1, np.int32))
     for nq, k in ((256, 32), (1, 5)):
         q = to_bf16_bits(rng.standard_normal((nq, d)).astype(np.float32))
-        for scoped in (False, True):
-            qu = np.full(nq, 3, np.int32) if scoped else None
+        for scoped in (False, True, "mixed"):
+            if scoped == "mixed" and nq == 1:
+                continue
+            qu = (rng.integers(0, 10, nq).astype(np.int32) if scoped == "mixed" else np.full(nq, 3, np.int32)) if scoped else None
             for _ in range(5):
                 ix.search(q, k, qu, None)
             t0 = time.perf_counter()
@@ -27,5 +29,5 @@ with Index(d, n) as ix:
                 ix.search(q, k, qu, None)
             wall = (time.perf_counter() - t0) / reps * 1e3
             st = ix.stats()
-            print(f"rows {n} nq {nq} k {k} scope {'user==3 (10% of rows)' if scoped else 'none'}: kernel {N.KERNEL_NAMES[st['last_kernel']]} "
+            print(f"rows {n} nq {nq} k {k} scope {('10 different users in one batch (row bit masks)' if scoped == 'mixed' else 'user==3 (10% of rows)') if scoped else 'none'}: kernel {N.KERNEL_NAMES[st['last_kernel']]} "
                   f"device {st['last_total_ms']:.3f} ms, host call {wall:.3f} ms, launches {st['last_launches']}", flush=True)
