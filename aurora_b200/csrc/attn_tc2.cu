@@ -41,10 +41,12 @@ constexpr int kQB = 128, kKB = 128, kSub = 64, kDh = 64;
 constexpr int kTile = 128 * kDh * 2;          // 16 KB: 128 rows x 128 B
 constexpr int kSlots = 2, kRing = 2;
 constexpr int kThreads = (2 * kSlots + 4 * kSlots) * 32;   // per slot: producer, MMA issuer, four softmax warps
-constexpr int kMaxUnits = 512;
+constexpr int kMaxUnits = 256;
+constexpr int kStageRow = 144;                                     // 128 B of one output row + 16 B pad (bank spread)
+constexpr int kStageWarp = 16 * kStageRow;                          // half a warp's rows at a time
 constexpr int kSlotSmem = (3 * kRing) * kTile;                     // Q ring + K ring + V ring (Q of the next item is prefetched)
 constexpr int kColS = 0, kColP = 128, kColO = 192, kSlotCols = 256;   // S0 S1 | P0 P1 | O
-constexpr size_t kSmemBytes = 1024 + static_cast<size_t>(kSlots) * kSlotSmem + 512 + kMaxUnits * 16;
+constexpr size_t kSmemBytes = 1024 + static_cast<size_t>(kSlots) * kSlotSmem + 512 + kMaxUnits * 16 + 4 * kSlots * kStageWarp;
 constexpr float kRescaleGap = 8.0f;
 
 // per slot: q_full[2], q_free[2], k_full[2], k_free[2], v_full[2], v_free[2], s_full[2], s_free[2], p_full[2], pv_done[2], o_free
@@ -85,13 +87,29 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __host__ __device__ constexpr uint32_t idesc_bf16_f32_bmn(int m, int n) { return idesc_bf16_f32(m, n) | (1u << 16); }
 
-// Bounded wait: false (and the CTA-wide abort flag set) after ~1 s.
+// Bounded wait: false (and the CTA-wide abort flag set) after 1 s.
+// The probe carries a suspend-time hint: a waiting warp is parked by the hardware (no issue slots taken from the
+// softmax warps sharing its scheduler) and woken when the phase completes.
+__device__ __forceinline__ bool mbar_test_park(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ bool wait_b(uint64_t* bar, uint32_t parity, volatile int* abort_flag) {
+  uint64_t t0 = 0;
   for (uint32_t spin = 0;; ++spin) {
-    if (mbar_test(bar, parity)) return true;
-    if ((spin & 255u) == 255u) {
+    if (mbar_test_park(bar, parity)) return true;
+    if ((spin & 15u) == 15u) {
       if (*abort_flag) return false;
-      if (spin > (1u << 25)) { *abort_flag = 1; return false; }
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 1000000000ull) { *abort_flag = 1; return false; }
     }
   }
 }
@@ -110,6 +128,57 @@ __device__ __forceinline__ Unit fetch_unit_global(const AttnParams& p, int w) {
 __device__ __forceinline__ Unit get_unit(const AttnParams& p, const int4* tab, int li, int G) {
   if (li < kMaxUnits) { const int4 v = tab[li]; Unit u; u.tok0 = v.x; u.len = v.y; u.q0 = v.z; u.head = v.w; return u; }
   return fetch_unit_global(p, li * G + static_cast<int>(blockIdx.x));
+}
+
+// Epilogue of one work item for one softmax warp: wait for the item's last PV, read O, hand the accumulator back, scale by
+// 1 / row sum and store.  Kept out of line: it runs once per item from two call sites and would otherwise triple the
+// softmax loop's footprint in the instruction cache.
+struct Pending { bool have, dead; uint32_t last; float sum; int tok, n_rows, head; };
+__device__ __noinline__ bool drain_item(const Pending& d, uint64_t* b, uint32_t trow, uint8_t* stage, int quarter, int lane,
+                                        const AttnParams& p, volatile int* abort_flag) {
+  if (!wait_b(&b[B_PVDONE + (d.last & 1)], (d.last >> 1) & 1, abort_flag)) return false;   // O complete: in-order pipe
+  tc_fence_after();
+  if (d.dead) {
+    if (lane == 0) mbar_arrive(&b[B_OFREE]);
+    return true;
+  }
+  const float inv = 1.0f / d.sum;
+  uint32_t o[2][32];
+  tmem_ld_x32(trow + kColO, o[0]);
+  tmem_ld_x32(trow + kColO + 32, o[1]);
+  tmem_wait_ld();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&b[B_OFREE]);                     // the next item's first PV may overwrite O
+  // 32 rows x 128 B, staged 16 rows at a time so that every store instruction writes four whole 128-byte rows
+  __nv_bfloat16* dst = p.ctx + static_cast<size_t>(d.tok + quarter * 32) * p.ld_ctx + d.head * kDh;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    if ((lane >> 4) == half) {
+      uint4* srow = reinterpret_cast<uint4*>(stage + (lane & 15) * kStageRow);
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          uint4 q4;
+          q4.x = pack_bf16x2(__uint_as_float(o[h][8 * e + 0]) * inv, __uint_as_float(o[h][8 * e + 1]) * inv);
+          q4.y = pack_bf16x2(__uint_as_float(o[h][8 * e + 2]) * inv, __uint_as_float(o[h][8 * e + 3]) * inv);
+          q4.z = pack_bf16x2(__uint_as_float(o[h][8 * e + 4]) * inv, __uint_as_float(o[h][8 * e + 5]) * inv);
+          q4.w = pack_bf16x2(__uint_as_float(o[h][8 * e + 6]) * inv, __uint_as_float(o[h][8 * e + 7]) * inv);
+          srow[h * 4 + e] = q4;
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = i * 4 + (lane >> 3), rg = half * 16 + r;      // row inside this warp's 32
+      const uint4 q4 = *reinterpret_cast<const uint4*>(stage + r * kStageRow + (lane & 7) * 16);
+      if (quarter * 32 + rg < d.n_rows)
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(dst + static_cast<size_t>(rg) * p.ld_ctx) + (lane & 7) * 16) = q4;
+    }
+    __syncwarp();
+  }
+  return true;
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -241,16 +310,20 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
   } else {
     // ================================================================ softmax warps (4 per slot)
     const int s = (warp - 2 * kSlots) >> 2, quarter = warp & 3;
-    const int row = quarter * 32 + lane;
     uint64_t* b = bars + s * B_COUNT;
     const uint32_t trow = tmem_base + s * kSlotCols + (static_cast<uint32_t>(quarter * 32) << 16);
     const float sc = p.scale_log2e;
-    uint32_t sbk = 0, items = 0;      // running sub-block / item counts of this slot (buffer index and barrier parities)
-    for (int li = s; li < n_local && !*abort_flag; li += kSlots, ++items) {
+    uint8_t* stage = smem + kSlots * kSlotSmem + 512 + kMaxUnits * 16 + (warp - 2 * kSlots) * kStageWarp;
+    uint32_t sbk = 0;                 // running sub-block count of this slot (buffer index and barrier parities)
+    // The epilogue of an item (wait for its last PV, read O, normalise, store) runs AFTER the first sub-block of the next
+    // item: that sub-block's scores are in TMEM long before, so the warp computes instead of idling on the tensor pipe.
+    Pending pend;
+    pend.have = false; pend.dead = false; pend.last = 0; pend.sum = 1.f; pend.tok = 0; pend.n_rows = 0; pend.head = 0;
+    bool ok = true;
+    for (int li = s; li < n_local && ok && !*abort_flag; li += kSlots) {
       const Unit u = get_unit(p, unit_tab, li, G);
       const int nsb = unit_nsb(u);
       float m_ref = -INFINITY, sum = 0.f;
-      bool ok = true;
       const bool dead = u.q0 + quarter * 32 >= u.len;              // all 32 query rows of this warp are padding
       for (int t = 0; t < nsb && ok; ++t, ++sbk) {
         const uint32_t buf = sbk & 1, use = sbk >> 1;
@@ -262,6 +335,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
           if (lane == 0) mbar_arrive(&b[B_SFREE + buf]);
           if (sbk >= 2) { ok = wait_b(&b[B_PVDONE + buf], (use - 1) & 1, abort_flag); if (!ok) break; }
           if (lane == 0) mbar_arrive(&b[B_PFULL + buf]);
+          if (t == 0 && pend.have) { ok = drain_item(pend, b, trow, stage, quarter, lane, p, abort_flag); pend.have = false; }
           continue;
         }
         tc_fence_after();
@@ -273,21 +347,22 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
         __syncwarp();
         if (lane == 0) mbar_arrive(&b[B_SFREE + buf]);            // S_{t+2} may overwrite this score buffer now
         const int nv = u.len - t * kSub;                           // valid keys in this sub-block (>= 1)
-        float mb = -INFINITY;
-        if (nv >= kSub) {                                          // full sub-block (all but a sequence's last): no masking
+        if (nv < kSub) {                                           // a sequence's last sub-block: keys past its end
 #pragma unroll
           for (int c = 0; c < 2; ++c)
 #pragma unroll
-            for (int e = 0; e < 32; e += 2) mb = max3(mb, __uint_as_float(v[c][e]), __uint_as_float(v[c][e + 1]));
-        } else {
-#pragma unroll
-          for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              if (c * 32 + e >= nv) v[c][e] = 0xFF800000u;         // -inf: P = 0 for keys past the sequence end
-              mb = fmaxf(mb, __uint_as_float(v[c][e]));
-            }
+            for (int e = 0; e < 32; ++e)
+              if (c * 32 + e >= nv) v[c][e] = 0xFF800000u;         // -inf: P = 0
         }
+        float mb = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int e = 0; e < 32; e += 8) {                       // independent chains
+            const float m0 = max3(__uint_as_float(v[c][e]), __uint_as_float(v[c][e + 1]), __uint_as_float(v[c][e + 2]));
+            const float m1 = max3(__uint_as_float(v[c][e + 3]), __uint_as_float(v[c][e + 4]), __uint_as_float(v[c][e + 5]));
+            mb = max3(mb, max3(m0, m1, __uint_as_float(v[c][e + 6])), __uint_as_float(v[c][e + 7]));
+          }
         mb *= sc;                                                  // log2 domain (sc > 0)
         // lazy rescale: only when this sub-block's maximum leaves the reference far behind
         const bool grow = mb > m_ref + kRescaleGap;
@@ -329,6 +404,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
           }
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
+            // (moving a quarter of these to an FMA-pipe polynomial, as MUFU-bound kernels do, measured 4-5 % SLOWER here:
+            //  the loop is issue/latency bound at two warps per scheduler, profiles/attn_ab_r2.txt)
             const float p0 = ex2_approx(fmaf(__uint_as_float(v[c][e]), sc, -m_ref));
             const float p1 = ex2_approx(fmaf(__uint_as_float(v[c][e + 1]), sc, -m_ref));
             s0 += p0; s1 += p1;
@@ -341,39 +418,13 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&b[B_PFULL + buf]);
+        if (t == 0 && pend.have) { ok = drain_item(pend, b, trow, stage, quarter, lane, p, abort_flag); pend.have = false; }
       }
       if (!ok) break;
-      // ---- item done: O complete once the last PV retired (the tensor pipe executes in issue order)
-      if (!wait_b(&b[B_PVDONE + ((sbk - 1) & 1)], ((sbk - 1) >> 1) & 1, abort_flag)) break;
-      tc_fence_after();
-      if (dead) {
-        if (lane == 0) mbar_arrive(&b[B_OFREE]);
-        continue;
-      }
-      const float inv = 1.0f / sum;
-      const bool live = u.q0 + row < u.len;
-      __nv_bfloat16* dst = p.ctx + static_cast<size_t>(u.tok0 + u.q0 + row) * p.ld_ctx + u.head * kDh;
-      uint32_t o[2][32];
-      tmem_ld_x32(trow + kColO, o[0]);
-      tmem_ld_x32(trow + kColO + 32, o[1]);
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&b[B_OFREE]);                     // the next item's first PV may overwrite O
-      if (live) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            uint4 q4;
-            q4.x = pack_bf16x2(__uint_as_float(o[h][8 * e + 0]) * inv, __uint_as_float(o[h][8 * e + 1]) * inv);
-            q4.y = pack_bf16x2(__uint_as_float(o[h][8 * e + 2]) * inv, __uint_as_float(o[h][8 * e + 3]) * inv);
-            q4.z = pack_bf16x2(__uint_as_float(o[h][8 * e + 4]) * inv, __uint_as_float(o[h][8 * e + 5]) * inv);
-            q4.w = pack_bf16x2(__uint_as_float(o[h][8 * e + 6]) * inv, __uint_as_float(o[h][8 * e + 7]) * inv);
-            reinterpret_cast<uint4*>(dst)[h * 4 + e] = q4;
-          }
-      }
+      pend.have = true; pend.dead = dead; pend.last = sbk - 1; pend.sum = sum;
+      pend.tok = u.tok0 + u.q0; pend.n_rows = u.len - u.q0; pend.head = u.head;
     }
+    if (ok && pend.have) drain_item(pend, b, trow, stage, quarter, lane, p, abort_flag);
   }
 
   tc_fence_before();
@@ -393,8 +444,7 @@ cudaError_t attn_tc2_launch(int sm_count, const void* tmap_qkv, const AttnParams
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const int units_per_cta = kSlots;
-  int grid = (total + units_per_cta - 1) / units_per_cta;
+  int grid = (total + kSlots - 1) / kSlots;
   if (grid > sm_count) grid = sm_count;
   return launch_pdl(attn_tc2_kernel, dim3(grid), dim3(kThreads), kSmemBytes, s, 1, *reinterpret_cast<const CUtensorMap*>(tmap_qkv), p);
 }

@@ -6,11 +6,13 @@
 //   inter  [max_tokens_pad, I]    FFN activation
 // and the TMA descriptors over them (activations as GEMM A operands, weights as B operands).
 // A forward is 2 + 7*L + 1 kernel launches on one stream; no CPU compute path exists.
+#include <algorithm>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -462,6 +464,8 @@ int aur_debug_attention(int32_t device, const uint16_t* qkv, const int32_t* cu, 
     if (len < 1 || len > 512) return report_error(AUR_ERR_INVALID, "sequence length %d", len);
     for (int q0 = 0; q0 < len; q0 += 128) items.push_back(AttnItem{cu[i], len, q0, 0});
   }
+  if (getenv("AUR_ATTN_SORT"))        // A/B timing only: longest-first order measured 3 % SLOWER than sequence order (profiles/attn_ab_r2.txt)
+    std::stable_sort(items.begin(), items.end(), [](const AttnItem& a, const AttnItem& b) { return a.len > b.len; });
   __nv_bfloat16 *dq = nullptr, *dc = nullptr; AttnItem* di = nullptr;
   int rc = AUR_OK;
   auto A = [&](auto** p, size_t cnt) { if (rc == AUR_OK) rc = dev_alloc(p, cnt); };

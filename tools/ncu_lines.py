@@ -32,3 +32,14 @@ print("%-28s %7s %6s %9s  long_sb wait short math sel notsel noinst branch" % ("
 for loc, a in sorted(agg.items(), key=lambda kv: -kv[1]["# Samples"])[:top]:
     print("%-28s %7d %5.1f%% %9d  %6d %5d %5d %4d %4d %5d %5d %5d" % ("%s:%d" % loc if loc else "?", a["# Samples"], 100.0 * a["# Samples"] / tot, a["Instructions Executed"],
           a["stall_long_sb"], a["stall_wait"], a["stall_short_sb"], a["stall_math"], a["stall_selected"], a["stall_not_selected"], a["stall_no_inst"], a["stall_branch_resolving"]))
+
+# call sites of the hottest inlined line (e.g. a wait helper): nearest following distinct source line
+if len(sys.argv) > 4:
+    hot = int(sys.argv[4])
+    print("\ninstances of line", hot)
+    for i, (loc, txt) in enumerate(ins):
+        n = int(rows[i][cols["# Samples"]])
+        if loc and loc[1] == hot and n > 40:
+            nxt = [ins[j][0][1] for j in range(i + 1, min(len(ins), i + 80)) if ins[j][0] and ins[j][0][0] == loc[0] and abs(ins[j][0][1] - hot) > 8]
+            prv = [ins[j][0][1] for j in range(max(0, i - 80), i) if ins[j][0] and ins[j][0][0] == loc[0] and abs(ins[j][0][1] - hot) > 8]
+            print("  sass %5d samples %5d executed %8s  prev %s next %s" % (i, n, rows[i][cols["Instructions Executed"]], prv[-2:], nxt[:2]))
