@@ -45,7 +45,16 @@ def configure_from_env() -> None:
         raise RuntimeError(f"vocabulary has {tok.vocab_size} entries, the model expects {cfg.vocab}")
     text_encoder = TextEncoder(enc, tok, max_len=cfg.max_pos)
     snap = os.environ.get("AURORA_B200_SNAPSHOT")
-    if snap and os.path.exists(os.path.join(snap, "meta.json")):
-        retriever.configure(factory=lambda: retriever.KnowledgeBase.load(snap, text_encoder, capacity=capacity, device=device))
-    else:
-        retriever.configure(encoder=text_encoder, capacity=capacity, device=device)
+    wal = os.environ.get("AURORA_B200_WAL", "1") != "0"      # mutation log beside the snapshot (replayed after a crash)
+
+    def make():
+        if snap and os.path.exists(os.path.join(snap, "meta.json")):
+            kb = retriever.KnowledgeBase.load(snap, text_encoder, capacity=capacity, device=device)
+        else:
+            kb = retriever.KnowledgeBase(text_encoder, capacity=capacity, device=device)
+        if snap and wal:
+            os.makedirs(snap, exist_ok=True)
+            kb.attach_wal(os.path.join(snap, "mutations.log"))
+        return kb
+
+    retriever.configure(factory=make)

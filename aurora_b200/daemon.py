@@ -26,7 +26,9 @@ in the window (the scope folds into the row scale, see csrc/capi.cu); each calle
 Durability.  The daemon owns the only copy of the vectors: it snapshots the knowledge base (KnowledgeBase.save:
 atomic rename of shard + metadata) after ``save_every`` mutations or ``save_seconds`` seconds with unsaved
 mutations, on SIGTERM / shutdown, and on the ``save`` call; it compacts tombstones when more than a quarter of the
-shard is dead.  The socket is created with mode 0600: any local process that can open it can read every tenant.
+shard is dead.  Between snapshots every acknowledged insert / delete is in the mutation log beside the snapshot
+(KnowledgeBase.attach_wal, fsync'd before the reply; bootstrap.configure_from_env attaches it): a restart loads the
+last snapshot and replays the log.  The socket is created with mode 0600: any local process that can open it can read every tenant.
 """
 
 from __future__ import annotations
@@ -455,6 +457,8 @@ if __name__ == "__main__":       # pragma: no cover
     ap.add_argument("--save-seconds", type=float, default=60.0, help="... or this long with unsaved mutations")
     ap.add_argument("--coalesce-us", type=int, default=200, help="gather concurrent searches for this long (0 = off)")
     a = ap.parse_args()
+    if a.snapshot:
+        os.environ["AURORA_B200_SNAPSHOT"] = a.snapshot      # the bootstrap restores from it and keeps the mutation log there
     if a.boot:
         mod, fn = a.boot.split(":")
         getattr(__import__(mod, fromlist=[fn]), fn)()

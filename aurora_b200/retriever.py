@@ -86,7 +86,11 @@ class KnowledgeBase:
         self._user_code: Dict[str, int] = {}
         self._org_code: Dict[str, int] = {}
         self.saved_mutations = 0
-        self.mutations = 0              # inserts + deletes since construction (the daemon's snapshot policy reads it)
+        self.mutations = 0              # inserts + deletes over the store's life (the daemon's snapshot policy reads it)
+        self._wal = None                # mutation log between snapshots (attach_wal)
+        self._wal_path: Optional[str] = None
+        self._wal_sync = True
+        self._replaying = False
 
     # ------------------------------------------------------------------ tenant codes
     def _code(self, table: Dict[str, int], key: Optional[str], create: bool) -> int:
@@ -97,6 +101,60 @@ class KnowledgeBase:
                 return -2  # matches no row
             table[key] = len(table)
         return table[key]
+
+    # ------------------------------------------------------------------ mutation log (durability between snapshots)
+    def attach_wal(self, path: str, sync: bool = True) -> int:
+        """Log every acknowledged mutation to ``path`` (JSON lines, fsync'd before the call returns) so that a crash
+        loses nothing a caller was told had been stored -- Weaviate keeps its own WAL on the data volume
+        (docker-compose.yaml:477-478).  Records already in the file that are newer than this store's state (a restart
+        after a crash: ``load`` restored the last snapshot) are replayed first: inserts re-encode their text -- the encoder
+        is deterministic -- deletes name the object keys.  ``save`` truncates the log.  Returns the replayed count."""
+        import json
+
+        with self._lock:
+            replayed = 0
+            if os.path.exists(path):
+                self._replaying = True
+                try:
+                    good = 0
+                    with open(path, "rb") as f:
+                        for raw in f:
+                            try:
+                                if not raw.endswith(b"\n"):
+                                    raise ValueError("no terminator")
+                                rec = json.loads(raw.decode("utf-8"))
+                            except ValueError:
+                                break                    # torn final record of a crash mid-write: never acknowledged
+                            good += len(raw)
+                            if int(rec.get("gen", -1)) < self.mutations:
+                                continue                 # already inside the snapshot this store was loaded from
+                            if rec["op"] == "put":
+                                self.insert_objects([tuple(o) for o in rec["objs"]], rec.get("user"), rec.get("org"))
+                            elif rec["op"] == "del":
+                                self._delete_keys(rec["keys"])
+                            replayed += 1
+                finally:
+                    self._replaying = False
+                if good < os.path.getsize(path):
+                    with open(path, "r+b") as f:       # drop the torn tail so that new records start on a fresh line
+                        f.truncate(good)
+            self._wal_path, self._wal_sync = path, sync
+            self._wal = open(path, "a", encoding="utf-8")
+            return replayed
+
+    def _log(self, rec: Dict[str, Any]) -> None:
+        if self._wal is None or self._replaying:
+            return
+        import json
+
+        self._wal.write(json.dumps(rec, separators=(",", ":")) + "\n")
+        self._wal.flush()
+        if self._wal_sync:
+            os.fsync(self._wal.fileno())
+
+    def _delete_keys(self, keys: List[str]) -> int:
+        ids = [self._key2id[k] for k in keys if k in self._key2id]
+        return self._delete_ids(ids)
 
     # ------------------------------------------------------------------ ingest
     def insert(self, user_id: str, document_id: str, source_filename: str, chunks: List[Dict[str, Any]],
@@ -130,6 +188,7 @@ class KnowledgeBase:
         fused = hasattr(self.encoder, "encode_append") and hasattr(self.index, "_h")   # CUDA encoder + CUDA shard
         vecs = None if fused else self.encoder.encode(texts)
         with self._lock:
+            gen = self.mutations
             ids = np.empty(len(objs), dtype=np.int64)
             for i, (key, _, _) in enumerate(objs):
                 if key not in self._key2id:
@@ -154,6 +213,7 @@ class KnowledgeBase:
                     self._by_org.setdefault(props["org_id"], set()).add(rid)
                 self.sparse.add(rid, text)
             self.mutations += len(objs)
+            self._log({"op": "put", "gen": gen, "user": user_id, "org": org_id, "objs": [list(o) for o in objs]})
         return len(objs)
 
     def _unindex(self, rid: int, props: Dict[str, Any]) -> None:
@@ -294,7 +354,8 @@ class KnowledgeBase:
             tmp_shard = os.path.join(directory, "shard.tmp")
             self.index.save(tmp_shard)
             os.replace(tmp_shard + ".npz", os.path.join(directory, f"shard.{gen}.npz"))
-            meta = {"shard": f"shard.{gen}.npz","version": 1, "dim": self.dim, "next_id": self._next_id, "user_code": self._user_code,
+            meta = {"shard": f"shard.{gen}.npz", "version": 1, "generation": gen, "dim": self.dim, "next_id": self._next_id,
+                    "user_code": self._user_code,
                     "org_code": self._org_code, "key2id": self._key2id,
                     "props": {str(k): v for k, v in self._props.items()}}
             tmp = os.path.join(directory, "meta.json.tmp")
@@ -308,6 +369,12 @@ class KnowledgeBase:
                     except OSError:
                         pass
             self.saved_mutations = gen
+            if self._wal is not None:               # everything logged so far is inside the snapshot: start a fresh log.
+                self._wal.close()                   # (a crash before this point leaves old records; replay skips them by gen)
+                tmp_wal = self._wal_path + ".tmp"
+                open(tmp_wal, "w").close()
+                os.replace(tmp_wal, self._wal_path)
+                self._wal = open(self._wal_path, "a", encoding="utf-8")
 
     @classmethod
     def load(cls, directory: str, encoder, capacity: int = 1 << 20, device: int = 0, index_loader=None,
@@ -332,6 +399,7 @@ class KnowledgeBase:
         loaded = index_loader(os.path.join(directory, meta.get("shard", "shard.npz")), int(capacity))
         kb = cls(encoder, capacity=capacity, device=device, index_factory=lambda dim, cap: loaded)
         kb._next_id = int(meta["next_id"])
+        kb.mutations = kb.saved_mutations = int(meta.get("generation", 0))     # the log's records are ordered by it
         kb._user_code = {k: int(v) for k, v in meta["user_code"].items()}
         kb._org_code = {k: int(v) for k, v in meta["org_code"].items()}
         kb._key2id = {k: int(v) for k, v in meta["key2id"].items()}
@@ -350,8 +418,13 @@ class KnowledgeBase:
 
     def delete_where(self, pred) -> int:
         with self._lock:
-            ids = self._matching_ids(pred)
+            return self._delete_ids(self._matching_ids(pred))
+
+    def _delete_ids(self, ids: List[int]) -> int:
+        with self._lock:
             if ids:
+                gen = self.mutations
+                keys = [self._id2key.get(rid) for rid in ids]
                 self.index.remove(np.array(ids, dtype=np.int64))
                 for rid in ids:
                     p = self._props.pop(rid)
@@ -359,6 +432,7 @@ class KnowledgeBase:
                     self.sparse.remove(rid)
                     self._key2id.pop(self._id2key.pop(rid, None), None)
                 self.mutations += len(ids)
+                self._log({"op": "del", "gen": gen, "keys": [k for k in keys if k]})
             return len(ids)
 
     def count_where(self, pred) -> int:

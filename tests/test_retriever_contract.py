@@ -2,6 +2,7 @@
 same names, keyword arguments, return shapes and error conventions.  CPU only (the vector
 index is a test double; the GPU-backed run of the same contract is in test_gpu_retriever.py)."""
 
+import os
 import inspect
 
 import pytest
@@ -190,6 +191,44 @@ def test_snapshot_roundtrip(tmp_path):
     assert b.query("unrelated", 3, user_id="u1", alpha=1.0)[0].properties["document_id"] == "d1"   # u2's chunk stays out of scope
     assert b.insert("u1", "d1", "a.md", _chunks("redis failover procedure v2")) == 1               # same uuid5 key -> upsert
     assert b.count_where(lambda p: p["document_id"] == "d1") == 2
+
+
+def test_mutation_log_replays_what_a_crash_would_lose(tmp_path):
+    """Snapshot, then more inserts / an upsert / deletes logged but never snapshotted, then "crash": a store loaded
+    from the old snapshot + the log answers exactly like the store that died; records already inside a snapshot are
+    skipped by generation; a torn final line is ignored; save() truncates the log."""
+    emb = HashEmbedder(64)
+    mk = lambda dim, cap: OracleIndex(dim, cap)   # noqa: E731
+    snap, wal = str(tmp_path / "snap"), str(tmp_path / "snap" / "mutations.log")
+    os.makedirs(snap)
+    a = R.KnowledgeBase(emb, capacity=256, index_factory=mk)
+    assert a.attach_wal(wal) == 0
+    a.insert("u1", "d1", "a.md", _chunks("redis failover procedure", "postgres vacuum tuning"), "org")
+    a.save(snap)
+    assert os.path.getsize(wal) == 0                                      # everything logged so far is in the snapshot
+    a.insert("u1", "d2", "b.md", _chunks("kafka lag alert zx77", "nginx 502 runbook"))
+    a.insert("u1", "d1", "a.md", _chunks("redis failover procedure, second edition"))      # upsert of (u1, d1, 0)
+    a.insert("u2", "d9", "z.md", _chunks("another tenant's notes"))
+    assert a.delete_where(lambda p: p["document_id"] == "d2" and p["chunk_index"] == 1) == 1
+    want = {q: [(o.properties["document_id"], o.properties["chunk_index"], o.properties["content"], round(o.metadata.score, 6))
+                for o in a.query(q, 5, user_id="u1", alpha=0.5)] for q in ("redis failover", "zx77 kafka", "nginx")}
+    with open(wal, "a") as f:
+        f.write('{"op":"put","gen":999,"objs":[["torn')               # the crash hit mid-record
+    b = R.KnowledgeBase.load(snap, emb, capacity=256, index_loader=lambda path, cap: OracleIndex.load(path, cap))
+    assert b.count_where(lambda p: True) == 2                             # the snapshot alone is stale
+    assert b.attach_wal(wal) == 4                                         # three puts + one delete
+    got = {q: [(o.properties["document_id"], o.properties["chunk_index"], o.properties["content"], round(o.metadata.score, 6))
+               for o in b.query(q, 5, user_id="u1", alpha=0.5)] for q in want}
+    assert got == want
+    assert b.count_where(lambda p: True) == a.count_where(lambda p: True) == 4 and b.mutations == a.mutations
+    assert b.query("another tenant", 3, user_id="u2", alpha=1.0)[0].properties["document_id"] == "d9"
+    assert open(wal).read().endswith("\n") and "torn" not in open(wal).read()   # the torn tail is gone: appends stay parseable
+    # a second restart from the same (old) snapshot replays again, a restart after a new snapshot replays nothing
+    c = R.KnowledgeBase.load(snap, emb, capacity=256, index_loader=lambda path, cap: OracleIndex.load(path, cap))
+    assert c.attach_wal(wal) == 4
+    c.save(snap)
+    d = R.KnowledgeBase.load(snap, emb, capacity=256, index_loader=lambda path, cap: OracleIndex.load(path, cap))
+    assert d.attach_wal(wal) == 0 and d.count_where(lambda p: True) == 4
 
 
 def test_filter_algebra():

@@ -1,2 +1,1 @@
-python tools/decompose.py 125000 gpurun_out/decompose_125k_r2.json 2>&1 | tail -14
-python tools/push_stats.py 125000 2>&1 | tail -12
+for n in 125000 1000000; do echo "== rows $n"; AURORA_B200_LIB=$PWD/aurora_b200/libaurora_b200_prof.so python tools/push_stats.py $n 2>&1 | tail -16; done | tee gpurun_out/push_stats_small_r2.txt
