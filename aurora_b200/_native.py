@@ -23,7 +23,7 @@ KERNEL_NAMES = {0: "auto", 1: "simt", 2: "tcgen05-cta1", 3: "tcgen05-cta2"}
 EXPORTS = [
     "aur_abi_version", "aur_last_error", "aur_device_count", "aur_open", "aur_close", "aur_get_stats",
     "aur_set_option", "aur_sync", "aur_add", "aur_add_dev", "aur_export", "aur_read_rows", "aur_compact", "aur_remove", "aur_search", "aur_search_ex", "aur_search_subset", "aur_search_dev",
-    "aur_merge_topk_dev", "aur_merge_topk_packed_dev", "aur_exchange_create", "aur_exchange_connect", "aur_exchange_close",
+    "aur_merge_topk_dev", "aur_merge_topk_packed_dev", "aur_merge_topk_host", "aur_exchange_create", "aur_exchange_connect", "aur_exchange_close",
     "aur_exchange_status", "aur_search_exchange_dev", "aur_cosine_pairs", "aur_dev_malloc", "aur_dev_free", "aur_memcpy_h2d", "aur_memcpy_d2h",
     "aur_debug_tc_scores",
     "aur_encoder_open", "aur_encoder_close", "aur_encoder_load", "aur_encode", "aur_encode_append",
@@ -100,6 +100,7 @@ def load():
         "aur_search": (C.c_int, [vp, vp, i32, i32, vp, vp, vp, vp]),
         "aur_search_dev": (C.c_int, [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]),
         "aur_merge_topk_dev": (C.c_int, [i32, vp, vp, i32, i32, i32, vp, vp, vp, vp]),
+        "aur_merge_topk_host": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp]),
         "aur_merge_topk_packed_dev": (C.c_int, [i32, vp, i32, i32, i32, vp, vp, vp, vp]),
         "aur_exchange_create": (C.c_int, [i32, i32, i32, i32, i32, C.POINTER(vp), vp]),
         "aur_exchange_connect": (C.c_int, [vp, vp]),

@@ -47,11 +47,22 @@ def configure_from_env() -> None:
     snap = os.environ.get("AURORA_B200_SNAPSHOT")
     wal = os.environ.get("AURORA_B200_WAL", "1") != "0"      # mutation log beside the snapshot (replayed after a crash)
 
+    # AURORA_B200_DEVICES = "all" or "0,1,2,...": this process owns one shard per listed GPU (engine.MultiIndex);
+    # the encoder stays on AURORA_B200_DEVICE
+    devs = os.environ.get("AURORA_B200_DEVICES", "").strip()
+    factory = loader = None
+    if devs:
+        from .engine import MultiIndex
+
+        devices = None if devs == "all" else [int(x) for x in devs.split(",")]
+        factory = lambda dim, cap: MultiIndex(dim, cap, devices=devices)                    # noqa: E731
+        loader = lambda path, cap: MultiIndex.load(path, capacity=cap, devices=devices)     # noqa: E731
+
     def make():
         if snap and os.path.exists(os.path.join(snap, "meta.json")):
-            kb = retriever.KnowledgeBase.load(snap, text_encoder, capacity=capacity, device=device)
+            kb = retriever.KnowledgeBase.load(snap, text_encoder, capacity=capacity, device=device, index_loader=loader)
         else:
-            kb = retriever.KnowledgeBase(text_encoder, capacity=capacity, device=device)
+            kb = retriever.KnowledgeBase(text_encoder, capacity=capacity, device=device, index_factory=factory)
         if snap and wal:
             os.makedirs(snap, exist_ok=True)
             kb.attach_wal(os.path.join(snap, "mutations.log"))

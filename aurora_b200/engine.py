@@ -191,6 +191,129 @@ class Index:
         return {f: getattr(st, f) for f, _ in N.AurStats._fields_}
 
 
+class MultiIndex:
+    """One process, one shard per GPU of the host (the daemon's deployment on an 8-GPU box): the corpus is row-sharded
+    by ``id mod n`` -- an upsert or a delete always lands on the shard that holds the old row -- every search runs on
+    all shards at once (one host thread per device; the C calls release the GIL) and the per-shard top-k lists are
+    merged on the host by (score desc, id asc), the order the device merge uses (csrc/kernels_simt.cu merge_topk_kernel).
+    Same surface as ``Index`` for what ``retriever.KnowledgeBase`` and the daemon call.  The rank-per-GPU deployment with
+    the fused peer-store exchange (sharded.ShardedIndex) stays the throughput path; this one trades ~0.1 ms of host
+    merge for a single owner process.  ``shard_factory(dim, capacity, device)`` builds one shard (tests: a CPU double)."""
+
+    def __init__(self, dim: int, capacity: int, devices=None, dtype: str = "bf16", shard_factory=None, _shards=None):
+        from concurrent.futures import ThreadPoolExecutor
+
+        if devices is None:
+            devices = list(range(N.load().aur_device_count()))
+        if not devices:
+            raise RuntimeError("MultiIndex needs at least one device")
+        self.dim, self.capacity, self.devices = int(dim), int(capacity), [int(d) for d in devices]
+        n = len(self.devices)
+        per = (self.capacity + n - 1) // n
+        per += max(64, per // 8)                    # id mod n is balanced only statistically
+        self._native_merge = shard_factory is None and _shards is None
+        if shard_factory is None:
+            shard_factory = lambda dim_, cap_, dev_: Index(dim_, cap_, dtype=dtype, device=dev_)   # noqa: E731
+        self.shards = _shards if _shards is not None else [shard_factory(self.dim, per, d) for d in self.devices]
+        self.dtype = getattr(self.shards[0], "dtype", N.AUR_BF16)
+        self._pool = ThreadPoolExecutor(max_workers=n, thread_name_prefix="aurora-b200-shard")
+
+    # -------------------------------------------------------------- plumbing
+    def _each(self, fn):
+        """fn(shard index, shard) on every shard concurrently; results in shard order."""
+        if len(self.shards) == 1:
+            return [fn(0, self.shards[0])]
+        return list(self._pool.map(lambda t: fn(*t), enumerate(self.shards)))
+
+    def _split(self, ids: np.ndarray):
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        owner = np.mod(ids, len(self.shards))
+        return ids, [np.nonzero(owner == s)[0] for s in range(len(self.shards))]
+
+    def _merge(self, parts, k: int):
+        if len(parts) == 1:
+            return parts[0]
+        if self._native_merge:      # k-way merge of the sorted lists in C (csrc/host_merge.cpp): microseconds
+            ids = np.ascontiguousarray(np.stack([p[0] for p in parts]), dtype=np.int64)
+            sc = np.ascontiguousarray(np.stack([p[1] for p in parts]), dtype=np.float32)
+            nq, k_in = ids.shape[1], ids.shape[2]
+            out_s, out_i = np.empty((nq, k), dtype=np.float32), np.empty((nq, k), dtype=np.int64)
+            N.check(N.load().aur_merge_topk_host(_ptr(sc), _ptr(ids), len(parts), nq, k_in, k, _ptr(out_s), _ptr(out_i)))
+            return out_i, out_s
+        ids = np.concatenate([p[0] for p in parts], axis=1)         # CPU doubles in the tests: the same order in numpy
+        sc = np.concatenate([p[1] for p in parts], axis=1)
+        key_id = np.where(ids < 0, np.iinfo(np.int64).max, ids)      # empty slots last
+        order = np.lexsort((key_id, -sc.astype(np.float64)), axis=1)[:, :k]
+        return np.take_along_axis(ids, order, axis=1), np.take_along_axis(sc, order, axis=1)
+
+    # -------------------------------------------------------------- ingest / deletes
+    def add(self, rows: np.ndarray, ids: np.ndarray, user_codes=None, org_codes=None) -> None:
+        rows = np.asarray(rows)
+        ids, sel = self._split(ids)
+        u = None if user_codes is None else np.asarray(user_codes, dtype=np.int32)
+        o = None if org_codes is None else np.asarray(org_codes, dtype=np.int32)
+
+        def put(s, shard):
+            ix = sel[s]
+            if len(ix):
+                shard.add(rows[ix], ids[ix], None if u is None else u[ix], None if o is None else o[ix])
+        self._each(put)
+
+    def remove(self, ids) -> int:
+        ids, sel = self._split(ids)
+        return int(sum(self._each(lambda s, shard: shard.remove(ids[sel[s]]) if len(sel[s]) else 0)))
+
+    # -------------------------------------------------------------- search
+    def search(self, queries: np.ndarray, k: int, q_user=None, q_org=None):
+        return self._merge(self._each(lambda s, shard: shard.search(queries, k, q_user, q_org)), k)
+
+    def search_subset(self, queries: np.ndarray, k: int, allow_ids: np.ndarray):
+        allow, sel = self._split(allow_ids)
+        return self._merge(self._each(lambda s, shard: shard.search_subset(queries, k, allow[sel[s]])), k)
+
+    # -------------------------------------------------------------- maintenance
+    def stats(self) -> dict:
+        per = self._each(lambda s, shard: shard.stats())
+        out = {key: int(sum(p.get(key, 0) for p in per)) for key in ("rows", "live", "searches")}
+        out["last_kernel"] = per[0].get("last_kernel", 0)
+        out["shards"] = len(per)
+        out["rows_per_shard"] = [int(p.get("rows", 0)) for p in per]
+        return out
+
+    def compact(self) -> int:
+        return int(sum(self._each(lambda s, shard: shard.compact())))
+
+    def sync(self) -> None:
+        self._each(lambda s, shard: shard.sync())
+
+    def save(self, path: str) -> None:
+        """One .npz like Index.save (live rows of all shards): a snapshot restores onto any number of devices."""
+        parts = self._each(lambda s, shard: shard.export())
+        cat = lambda i: np.concatenate([np.asarray(p[i])[p[4]] for p in parts])   # noqa: E731
+        np.savez(path, rows=cat(0), ids=cat(1), user=cat(2), org=cat(3), dim=self.dim, dtype=self.dtype, capacity=self.capacity)
+
+    @classmethod
+    def load(cls, path: str, capacity: Optional[int] = None, devices=None, shard_factory=None) -> "MultiIndex":
+        z = np.load(path if path.endswith(".npz") else path + ".npz")
+        dtype = "bf16" if int(z["dtype"]) == N.AUR_BF16 else "f32"
+        mi = cls(int(z["dim"]), int(capacity or z["capacity"]), devices=devices, dtype=dtype, shard_factory=shard_factory)
+        if len(z["ids"]):
+            mi.add(z["rows"], z["ids"], z["user"], z["org"])
+        return mi
+
+    def close(self) -> None:
+        for sh in self.shards:
+            sh.close()
+        self.shards = []
+        self._pool.shutdown(wait=False)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
 def merge_topk_packed_dev(device: int, packed_ptr: int, n_shards: int, nq: int, k: int, out_scores_ptr: int,
                           out_ids_ptr: int, out_scores64_ptr: int = 0, stream: int = 0) -> None:
     """packed: [n_shards][2][nq][k] 8-byte words (plane 0 fp64 scores, plane 1 int64 ids)."""

@@ -177,6 +177,13 @@ int aur_merge_topk_packed_dev(int32_t device, const void* packed, int32_t n_shar
                               int32_t k, float* out_scores, int64_t* out_ids,
                               double* out_scores64, void* stream);
 
+/* Host-side k-way merge of per-shard lists for a single owner process that holds one shard per GPU (each shard
+ * answered through aur_search from its own host thread): scores / ids are [n_lists][nq][k_in], each list sorted by
+ * (score desc, id asc) with id < 0 padding at its end; out is [nq][k_out] in the same order.  n_lists <= 64.
+ * Stands in for the coordinator-side merge of a multi-shard Weaviate class (weaviate_client.py:252-259 call site). */
+int aur_merge_topk_host(const float* scores, const int64_t* ids, int32_t n_lists, int32_t nq, int32_t k_in,
+                        int32_t k_out, float* out_scores, int64_t* out_ids);
+
 /* Fused exchange ("fused variant"): instead of a local top-k array + ncclAllGather + merge, the
  * kernel that produces a shard's exact top-k stores it straight into EVERY rank's exchange buffer over NVLink
  * (peer-mapped through CUDA IPC) as 8-byte words that each carry 4 bytes of payload and a 4-byte sequence tag, and the

@@ -80,5 +80,21 @@ class OracleIndex:
             ix.add(z["rows"], z["ids"], z["user"], z["org"])
         return ix
 
+    def export(self):
+        return self.rows, self.ids, self.user, self.org, self.live
+
+    def stats(self):
+        return {"rows": int(len(self.ids)), "live": int(self.live.sum()), "searches": 0, "last_kernel": 0}
+
+    def compact(self):
+        dead = int((~self.live).sum())
+        keep = self.live
+        self.rows, self.ids, self.user, self.org = self.rows[keep], self.ids[keep], self.user[keep], self.org[keep]
+        self.live = np.ones(len(self.ids), dtype=bool)
+        return dead
+
+    def sync(self):
+        pass
+
     def close(self):
         pass

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from aurora_b200 import _native as N
-from aurora_b200.engine import DeviceBuffer, Index, cosine_pairs, merge_topk_dev, merge_topk_packed_dev, to_bf16_bits
+from aurora_b200.engine import DeviceBuffer, Index, MultiIndex, cosine_pairs, merge_topk_dev, merge_topk_packed_dev, to_bf16_bits
 from oracle import cosine_topk as O
 
 pytestmark = pytest.mark.gpu
@@ -555,3 +555,51 @@ def test_compaction_reclaims_tombstones(dtype):
         assert len(order) == int(live.sum())
     ref_ids, ref_sc = O.cosine_topk(Q, C2, k, live=live)
     _check(ids2, sc2, ref_ids, ref_sc)
+
+
+# ------------------------------------------------------------------ one owner process, several shards
+def test_multi_index_one_process_many_shards():
+    """engine.MultiIndex: one shard per GPU of the box (three shards on the one GPU when there is only one), searched from
+    one host thread each and merged on the host -- against the oracle over the whole corpus, with tenant scopes,
+    upserts, deletes, a subset pre-filter and concurrent callers."""
+    import threading
+
+    n_dev = N.load().aur_device_count()
+    devices = list(range(n_dev)) if n_dev > 1 else [0, 0, 0]
+    n, d, nq, k = 60000, 768, 40, 16
+    C, Q = _data(n, d, nq, seed=321)
+    rng = np.random.default_rng(8)
+    ids = (rng.permutation(4 * n)[:n]).astype(np.int64)
+    ru, ro = rng.integers(0, 6, n).astype(np.int32), rng.integers(-1, 3, n).astype(np.int32)
+    live = np.ones(n, dtype=bool)
+    with MultiIndex(d, n + 1000, devices=devices) as mi:
+        mi.add(C[:35000], ids[:35000], ru[:35000], ro[:35000])
+        mi.add(C[35000:], ids[35000:], ru[35000:], ro[35000:])
+        st = mi.stats()
+        assert st["rows"] == n and st["shards"] == len(devices) and min(st["rows_per_shard"]) > n // len(devices) * 0.9
+        got = mi.search(Q, k)
+        _check(*got, *O.cosine_topk(Q, C, k, ids=ids))
+        gone = ids[11:9000:13]
+        assert mi.remove(gone) == len(gone)
+        live[11:9000:13] = False
+        C2 = C.copy(); C2[20000:20050] = O.round_to_bf16(C[20000:20050] * 0.25 + 0.5)        # upsert 50 rows
+        mi.add(C2[20000:20050], ids[20000:20050], ru[20000:20050], ro[20000:20050])
+        qu = np.full(nq, 3, np.int32); qo = np.full(nq, 1, np.int32)
+        _check(*mi.search(Q, k, qu, qo), *O.cosine_topk(Q, C2, k, ids=ids, live=live, row_user=ru, row_org=ro, q_user=qu, q_org=qo))
+        allow = ids[rng.permutation(n)[:5000]]
+        sub_live = live & np.isin(ids, allow)
+        _check(*mi.search_subset(Q, k, allow), *O.cosine_topk(Q, C2, k, ids=ids, live=sub_live))
+        want = O.cosine_topk(Q, C2, k, ids=ids, live=live)
+        errs = []
+
+        def caller():
+            try:
+                for _ in range(5):
+                    _check(*mi.search(Q, k), *want)
+            except Exception as e:       # pragma: no cover
+                errs.append(e)
+        ts = [threading.Thread(target=caller) for _ in range(4)]
+        [t.start() for t in ts]; [t.join() for t in ts]
+        assert not errs, errs[0]
+        assert mi.compact() == int((~live).sum()) + 50
+        _check(*mi.search(Q, k), *want)
