@@ -567,12 +567,30 @@ int search_host(aur_index* ix, const void* queries_host, int32_t nq, int32_t k, 
       }
     }
   }
-  rc = search_enqueue(ix, c, c->stage_q.p, nq, k, sc, n_rows, c->stage_scores.p, c->stage_ids.p, nullptr, s);
+  // Pinned caller buffers are mapped into the device's address space (UVA): the re-rank kernel then writes its nq x k
+  // results straight into them over PCIe and the two device-to-host copies (a launch + ~8 us of latency each) disappear.
+  float* d_scores = c->stage_scores.p;
+  int64_t* d_ids = c->stage_ids.p;
+  bool direct = false;
+  static const bool no_direct = getenv("AUR_NO_DIRECT_OUT") != nullptr;     // A/B switch
+  if (!no_direct) {
+    cudaPointerAttributes as{}, ai{};
+    if (cudaPointerGetAttributes(&as, scores_out) == cudaSuccess && cudaPointerGetAttributes(&ai, ids_out) == cudaSuccess &&
+        as.type == cudaMemoryTypeHost && ai.type == cudaMemoryTypeHost && as.devicePointer && ai.devicePointer) {
+      d_scores = static_cast<float*>(as.devicePointer);
+      d_ids = static_cast<int64_t*>(ai.devicePointer);
+      direct = true;
+    } else {
+      cudaGetLastError();
+    }
+  }
+  rc = search_enqueue(ix, c, c->stage_q.p, nq, k, sc, n_rows, d_scores, d_ids, nullptr, s);
   if (rc != AUR_OK) { cudaStreamSynchronize(s); return rc; }
-  // straight into the caller's buffers (async when they are pinned); nothing is written
-  // unless every kernel above was enqueued successfully
-  CU_TRY(cudaMemcpyAsync(scores_out, c->stage_scores.p, nout * 4, cudaMemcpyDeviceToHost, s));
-  CU_TRY(cudaMemcpyAsync(ids_out, c->stage_ids.p, nout * 8, cudaMemcpyDeviceToHost, s));
+  if (!direct) {
+    // into the caller's pageable buffers; nothing is written unless every kernel above was enqueued successfully
+    CU_TRY(cudaMemcpyAsync(scores_out, c->stage_scores.p, nout * 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(ids_out, c->stage_ids.p, nout * 8, cudaMemcpyDeviceToHost, s));
+  }
   CU_TRY(cudaStreamSynchronize(s));
   if (snapshot_out) *snapshot_out = n_rows;
   return AUR_OK;

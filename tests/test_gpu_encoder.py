@@ -93,6 +93,29 @@ def test_attention_matches_numpy(heads, lens):
     assert np.abs(got - ref).max() <= np.abs(ref).max() * 2 ** -7 + 1e-3   # P is rounded to bf16 before P.V
 
 
+def test_attention_many_units_per_cta():
+    """A batch large enough that every CTA's work list outgrows the shared-memory unit table of attn_tc2_kernel
+    (256 units per CTA; 2 000 sequences x 2 query blocks x 12 heads = 48 000 units over 148 CTAs): the units past the
+    table are decoded from global memory.  Checked against numpy on a sample of sequences from the start, the middle
+    and the end of the batch."""
+    lib = N.load()
+    heads, hidden, n_seq = 12, 768, 2000
+    rng = np.random.default_rng(2024)
+    lens = rng.integers(129, 150, n_seq)
+    cu = np.zeros(n_seq + 1, dtype=np.int32)
+    cu[1:] = np.cumsum(lens)
+    T = int(cu[-1])
+    qkv_bits = to_bf16_bits((rng.standard_normal((T, 3 * hidden), dtype=np.float32) * 1.5))
+    out = np.zeros((T, hidden), dtype=np.uint16)
+    N.check(lib.aur_debug_attention(0, _ptr(qkv_bits), _ptr(cu), n_seq, heads, hidden, _ptr(out), None))
+    for s in list(range(0, 6)) + list(range(990, 1000)) + list(range(n_seq - 6, n_seq)):
+        a, b = int(cu[s]), int(cu[s + 1])
+        qkv = bf16_bits_to_f32(qkv_bits[a:b])
+        ref = _attn_ref(qkv, np.array([0, b - a]), heads, hidden)
+        got = bf16_bits_to_f32(out[a:b]).astype(np.float64)
+        assert np.abs(got - ref).max() <= np.abs(ref).max() * 2 ** -7 + 1e-3, s
+
+
 def _check_pooled(got, ref):
     cos = (got * ref).sum(axis=1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(ref, axis=1))
     print(f"pooled parity: min cosine {cos.min():.6f}, max |d| {np.abs(got - ref).max():.2e}")     # (pytest -s / on failure)

@@ -603,3 +603,25 @@ def test_multi_index_one_process_many_shards():
         assert not errs, errs[0]
         assert mi.compact() == int((~live).sum()) + 50
         _check(*mi.search(Q, k), *want)
+
+
+def test_results_written_straight_into_pinned_host_buffers():
+    """aur_search with page-locked result buffers: the re-rank kernel writes through the UVA mapping (no device-to-host
+    copies); same answer as with pageable buffers, including a multi-pass batch (> 1024 queries) and the generic kernel."""
+    import ctypes as C
+    torch = pytest.importorskip("torch")
+
+    n, d, k = 30000, 768, 24
+    for nq, kernel in ((70, N.KERNEL_AUTO), (1300, N.KERNEL_AUTO), (9, N.KERNEL_SIMT)):
+        C_, Q = _data(n, d, nq, seed=nq)
+        with Index(d, n) as ix:
+            ix.add(C_, np.arange(n, dtype=np.int64))
+            ix.set_kernel(kernel)
+            want_ids, want_sc = ix.search(Q, k)                       # numpy (pageable) buffers
+            q = torch.from_numpy(to_bf16_bits(Q).view(np.int16)).pin_memory()
+            h_sc = torch.full((nq, k), float("nan"), dtype=torch.float32).pin_memory()
+            h_id = torch.full((nq, k), -7, dtype=torch.int64).pin_memory()
+            N.check(ix._lib.aur_search(ix._h, C.c_void_p(q.data_ptr()), nq, k, None, None, C.c_void_p(h_sc.data_ptr()),
+                                       C.c_void_p(h_id.data_ptr())))
+            assert np.array_equal(h_id.numpy(), want_ids) and np.array_equal(h_sc.numpy(), want_sc)
+        _check(want_ids, want_sc, *O.cosine_topk(Q, C_, k))
