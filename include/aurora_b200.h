@@ -135,8 +135,11 @@ int aur_remove(aur_index* ix, const int64_t* ids, int64_t n, int64_t* removed);
  * nq queries at once, top-k each.  q_user / q_org: per-query tenant codes (NULL q_user =
  * unfiltered; q_org may be NULL or hold -1 for "no org").  When every query of the batch
  * carries the same scope (the reference's call pattern) the tensor-core kernel serves it;
- * mixed scopes fall back to the generic kernel.
- * scores_out [nq*k] float, ids_out [nq*k] int64. */
+ * a batch with up to 32 distinct scopes rides on the same kernel through per-row bit masks,
+ * more fall back to the generic kernel.
+ * scores_out [nq*k] float, ids_out [nq*k] int64.  When both are page-locked (cudaHostAlloc /
+ * cudaHostRegister / torch pin_memory) the results are written into them by the device itself,
+ * without device-to-host copies; pageable buffers work the same, one staging copy slower. */
 int aur_search(aur_index* ix, const void* queries_host, int32_t nq, int32_t k,
                const int32_t* q_user, const int32_t* q_org,
                float* scores_out, int64_t* ids_out);
