@@ -270,6 +270,7 @@ int aur_tokenize(aur_tokenizer* t, const char* texts_utf8, const int64_t* offset
     if (total > 0x7FFFFFFFll) return aur::report_error(AUR_ERR_INVALID, "more than 2^31 tokens in one call");
     cu_seqlens_out[i + 1] = static_cast<int32_t>(total);
   }
+  if (!tokens_out && tokens_cap == 0) return AUR_OK;      // count mode: only the lengths (cu_seqlens_out) were asked for
   if (total > tokens_cap || (total > 0 && !tokens_out))
     return aur::report_error(AUR_ERR_NOMEM, "tokens_out holds %lld ids, %lld needed (n_texts * max_len always suffices)", (long long)tokens_cap, (long long)total);
   for (int32_t i = 0; i < n_texts; ++i)

@@ -181,6 +181,18 @@ class TextEncoder:
             seqs.append(ids if len(ids) <= max_len else ids[: max_len - 1] + ids[-1:])
         return pack_sequences(seqs)
 
+    def _over_long(self, texts: Sequence[str], lens: np.ndarray) -> List[int]:
+        """Indices of the texts whose full tokenisation exceeds the position table.  Only texts that came back at
+        exactly ``max_len`` ids can have been truncated; those are re-measured without the limit -- with the native
+        tokenizer in ONE C call for all of them."""
+        cand = [int(i) for i in np.nonzero(np.asarray(lens) >= self.max_len)[0]]
+        if not cand:
+            return []
+        if self._native and hasattr(self._tok, "lengths"):
+            full = self._tok.lengths([texts[i] for i in cand])
+            return [i for i, n in zip(cand, full) if n > self.max_len]
+        return [i for i in cand if len(self._windows(texts[i])) > 1]
+
     def _windows(self, text: str):
         """Token windows of one over-long text: [CLS] body[i : i + max_len - 2] [SEP]."""
         tok, cu = self._tokenize([text], 1 << 20) if self._native else pack_sequences([list(self._tok(text))])
@@ -203,19 +215,33 @@ class TextEncoder:
         return out
 
     def _encode_long(self, text: str) -> np.ndarray:
-        wins = self._windows(text)
+        return self._encode_long_many([text])[0]
+
+    def _encode_long_many(self, texts: Sequence[str]) -> np.ndarray:
+        """Vectors of over-long texts: all their windows go through the encoder as ONE packed batch, then each text's
+        windows are averaged (and re-normalised when the encoder normalises)."""
+        wins, owner = [], []
+        for t, text in enumerate(texts):
+            w = self._windows(text)
+            wins += w
+            owner += [t] * len(w)
         tok, cu = pack_sequences(wins)
-        v = self._encode_packed_any(tok, cu).mean(axis=0)
-        n = float(np.linalg.norm(v))
-        return v / n if (self._enc.cfg.normalize and n > 0) else v
+        vecs = self._encode_packed_any(tok, cu)
+        owner = np.asarray(owner)
+        out = np.empty((len(texts), self.dim), dtype=np.float32)
+        for t in range(len(texts)):
+            v = vecs[owner == t].mean(axis=0)
+            n = float(np.linalg.norm(v))
+            out[t] = v / n if (self._enc.cfg.normalize and n > 0) else v
+        return out
 
     # ------------------------------------------------------------------ API used by the retriever
     def encode(self, texts: Sequence[str]) -> np.ndarray:
         tok, cu = self._tokenize(texts, self.max_len)
         out = self._encode_packed_any(tok, cu)
-        for i in np.nonzero(np.diff(cu) >= self.max_len)[0]:          # possibly truncated: look again without the limit
-            if len(self._windows(texts[i])) > 1:
-                out[i] = self._encode_long(texts[i])
+        long_ones = self._over_long(texts, np.diff(cu))               # truncated above: windows, averaged
+        if long_ones:
+            out[long_ones] = self._encode_long_many([texts[i] for i in long_ones])
         return out
 
     def encode_append(self, index, texts: Sequence[str], ids: np.ndarray, user_codes=None, org_codes=None) -> None:
@@ -224,7 +250,7 @@ class TextEncoder:
         ids = np.ascontiguousarray(ids, dtype=np.int64)
         tok, cu = self._tokenize(texts, self.max_len)
         lens = np.diff(cu)
-        long_ones = [int(i) for i in np.nonzero(lens >= self.max_len)[0] if len(self._windows(texts[int(i)])) > 1]
+        long_ones = self._over_long(texts, lens)
         u = None if user_codes is None else np.ascontiguousarray(user_codes, dtype=np.int32)
         o = None if org_codes is None else np.ascontiguousarray(org_codes, dtype=np.int32)
         keep = np.ones(len(texts), dtype=bool)
@@ -245,9 +271,9 @@ class TextEncoder:
                 t, c = pack_sequences([tok[cu[x]:cu[x + 1]] for x in part])
             self._enc.encode_append(index, t, c, ids[part], None if u is None else u[part], None if o is None else o[part])
             i = j
-        for i in long_ones:                                           # averaged windows: the vector is formed on the host
-            v = self._encode_long(texts[i])[None, :]
-            index.add(v, ids[i:i + 1], None if u is None else u[i:i + 1], None if o is None else o[i:i + 1])
+        if long_ones:                                                 # averaged windows: the vectors are formed on the host
+            v = self._encode_long_many([texts[i] for i in long_ones])
+            index.add(v, ids[long_ones], None if u is None else u[long_ones], None if o is None else o[long_ones])
 
     def _append_texts_native(self, index, texts, ids, u, o) -> None:
         """The same ingest as ONE C call (aur_encode_text_append: tokenise + batches + append inside the library), for

@@ -164,6 +164,19 @@ class NativeTokenizer:
                                              tokens.ctypes.data_as(C.c_void_p), tokens.size, cu.ctypes.data_as(C.c_void_p), int(threads)))
         return tokens[: int(cu[-1])], cu
 
+    def lengths(self, texts, max_len: int = 1 << 20, threads: int = 0):
+        """Token counts ([CLS] / [SEP] included, capped at ``max_len``) of every text, one C call, no ids returned."""
+        import ctypes as C
+
+        import numpy as np
+
+        blob, offs = self._pack(texts)
+        n = len(offs) - 1
+        cu = np.zeros(n + 1, dtype=np.int32)
+        self._N.check(self._lib.aur_tokenize(self._h, blob, offs.ctypes.data_as(C.c_void_p), n, int(max_len), None, 0,
+                                             cu.ctypes.data_as(C.c_void_p), int(threads)))
+        return np.diff(cu)
+
     def encode_batch(self, texts, max_len: int = 512) -> List[List[int]]:
         tok, cu = self.encode_packed(texts, max_len)
         return [tok[cu[i]:cu[i + 1]].tolist() for i in range(len(cu) - 1)]

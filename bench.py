@@ -798,6 +798,11 @@ def text_ingest_leg(torch, dist, world, rank, dev, enc, ix, cfg, n_seq, lens, nx
     pieces, texts = synth_vocab_and_texts(cfg.vocab, lens, 4242 + rank)
     tok = NativeTokenizer(pieces)
     te = TextEncoder(enc, tok)
+    for i in np.nonzero(tok.lengths(texts) > 512)[0]:          # the generator's counts are approximate: like the token-id leg,
+        w = texts[i].split(" ")                                # no chunk is longer than the position table
+        while tok.lengths([" ".join(w)])[0] > 512:
+            w.pop()
+        texts[i] = " ".join(w)
     tk, cu_t = tok.encode_packed(texts, 512)
     big = texts * 8                                            # 1536 chunks: enough work for all cores
     tok.encode_packed(big, 512)

@@ -286,7 +286,8 @@ int aur_tokenizer_open_mem(const char* vocab_utf8, int64_t nbytes, int32_t lower
 int aur_tokenizer_close(aur_tokenizer* t);
 int aur_tokenizer_info(aur_tokenizer* t, int32_t* vocab_size, int32_t* unk_id, int32_t* cls_id, int32_t* sep_id);
 /* Every text -> [CLS] pieces [SEP] truncated to max_len ids, packed: tokens_out (capacity tokens_cap; n_texts * max_len
- * always suffices) and cu_seqlens_out [n_texts + 1].  n_threads 0 = all host cores. */
+ * always suffices) and cu_seqlens_out [n_texts + 1].  n_threads 0 = all host cores.  tokens_out = NULL with
+ * tokens_cap = 0 asks for the lengths only (cu_seqlens_out is filled, no ids are written). */
 int aur_tokenize(aur_tokenizer* t, const char* texts_utf8, const int64_t* offsets, int32_t n_texts, int32_t max_len,
                  int32_t* tokens_out, int64_t tokens_cap, int32_t* cu_seqlens_out, int32_t n_threads);
 /* Text in, rows in the shard: tokenise, encoder forward, append -- insert_chunks (weaviate_client.py:136-212) without

@@ -97,6 +97,10 @@ def test_native_truncation_packing_and_threads(pair):
     assert nat.encode(texts[0], max_len=16) == hf(texts[0], truncation=True, max_length=16)["input_ids"]
     with pytest.raises(Exception):
         nat.encode_packed(["x"], max_len=1)
+    # count mode (tokens_out = NULL): the lengths alone, with and without the limit
+    assert np.array_equal(nat.lengths(texts, max_len=512), lens)
+    full = nat.lengths(texts)
+    assert full[0] == len(hf(texts[0])["input_ids"]) > 512 and np.array_equal(full[1:4], lens[1:4])
 
 
 def test_cased_vocabulary_keeps_case_and_accents():
