@@ -193,12 +193,14 @@ def verify_distributed(dist, world, rank, dev, cfg, my_chunks, q_dev, got_ids, g
 
 # ----------------------------------------------------------------------------- CPU arm
 def cpu_flat_index(cfg, n_rows: int, threads: int = 0):
-    """Threaded fp32 flat cosine index over the same synthetic shape (seeded on the host), normalised at import."""
+    """Threaded fp32 flat cosine index over the same synthetic shape (seeded on the host), normalised at import.
+    Default thread count = physical cores (half the logical CPUs): sgemm on all 128 hyper-threads of the bench box
+    measured 3x SLOWER than on its 64 cores, and both CPU legs must be the CPU's best."""
     import torch
 
     from oracle.streaming_topk import FlatIndexF32
 
-    ix = FlatIndexF32(cfg["dim"], threads)
+    ix = FlatIndexF32(cfg["dim"], threads or max(1, (os.cpu_count() or 2) // 2))
     for gchunk, lo, m in chunk_plan(n_rows):
         g = torch.Generator().manual_seed(cfg["seed"] + gchunk)
         ix.add(torch.randn(m, cfg["dim"], generator=g, dtype=torch.float32))
