@@ -29,6 +29,24 @@ for d in (768, 1024):
                 for _ in range(3):
                     ids, sc = ix.search(Q, k)
                 assert np.array_equal(ids, want[0]), (d, nq, k, kern)
+        # round 2: mixed tenant scopes through the per-row bit masks, a resolved pre-filter, compaction, a batch
+        # past 256 queries (query super-blocks), results written straight into the caller's buffers
+        ru, ro = rng.integers(0, 5, n).astype(np.int32), rng.integers(-1, 2, n).astype(np.int32)
+    with Index(d, n + 64) as ix:
+        ix.add(C, np.arange(n, dtype=np.int64), ru, ro)
+        Q = O.round_to_bf16(rng.standard_normal((70, d)).astype(np.float32))
+        qu, qo = rng.integers(0, 5, 70).astype(np.int32), rng.integers(-1, 2, 70).astype(np.int32)
+        ids, sc = ix.search(Q, 16, qu, qo)
+        assert ix.stats()["last_kernel"] == N.KERNEL_TC2
+        assert np.array_equal(ids, O.cosine_topk(Q, C, 16, row_user=ru, row_org=ro, q_user=qu, q_org=qo)[0])
+        allow = np.arange(0, n, 3, dtype=np.int64)
+        live = np.zeros(n, bool); live[::3] = True
+        assert np.array_equal(ix.search_subset(Q, 16, allow)[0], O.cosine_topk(Q, C, 16, live=live)[0])
+        ix.remove(np.arange(0, n, 2, dtype=np.int64))
+        assert ix.compact() == n // 2
+        live = np.ones(n, bool); live[::2] = False
+        Qb = O.round_to_bf16(rng.standard_normal((600, d)).astype(np.float32))
+        assert np.array_equal(ix.search(Qb, 10)[0], O.cosine_topk(Qb, C, 10, live=live)[0])
     print("search ok", d, flush=True)
 
 cfg_o = B.BertConfig(hidden=128, layers=1, heads=2, inter=256, vocab=120, max_pos=512, pool="mean")
@@ -42,4 +60,5 @@ with Encoder(cfg, max_tokens=2048, max_seqs=8) as enc, Index(128, 32) as ix:
     assert np.abs(got - ref).max() < 1e-2
     enc.encode_append(ix, tok, cu, np.arange(5, dtype=np.int64))
     assert ix.stats()["live"] == 5
-print("encoder ok")
+print("encoder ok (attention v2)")
+
