@@ -230,7 +230,7 @@ finalize_kernel(FinalizeArgs a) {
     double qq = 0.0;
     for (int i = lane; i < a.dim; i += 32) { const double v = static_cast<double>(qs[i]); qq = fma(v, v, qq); }
     qq = warp_sum_lane0(qq);
-    if (lane == 0) s_qq = qq;
+    if (lane == 0) s_qq = sqrt(qq);          // |q|: one fp64 square root per query, not one per candidate
   }
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");     // the candidate lists come from the previous kernel
@@ -337,18 +337,28 @@ finalize_kernel(FinalizeArgs a) {
         }
       }
     }
+    // the kRe reduced (dot, |row|^2) pairs land in lanes 0 .. kRe-1, which then do the fp64 square root and division
+    // side by side (software sequences of a few hundred cycles each: one after the other on lane 0 they were a
+    // tenth of this kernel)
+    double my_d = 0.0, my_n2 = 0.0; int64_t my_id = -1; int my_row = -1;
 #pragma unroll
     for (int h = 0; h < kRe; ++h) {
-      const int c = c0 + h * nwarps;
-      if (c >= ncand) break;
-      double sc = -INFINITY; int64_t id = -1;
-      if (row[h] >= 0) {   // warp-uniform
-        const double d = warp_sum_lane0(dot[h]), n2 = warp_sum_lane0(cc[h]);
-        const double den = sqrt(s_qq) * sqrt(n2);
-        sc = den > 0.0 ? d / den : 0.0;  // zero norm -> 0.0 (similarity.py:94-95)
-        id = idv[h];
+      double d = 0.0, n2 = 0.0;
+      if (row[h] >= 0) { d = warp_sum_lane0(dot[h]); n2 = warp_sum_lane0(cc[h]); }   // warp-uniform
+      d = __shfl_sync(0xffffffffu, d, 0); n2 = __shfl_sync(0xffffffffu, n2, 0);
+      if (lane == h) { my_d = d; my_n2 = n2; my_id = idv[h]; my_row = row[h]; }
+    }
+    if (lane < kRe) {
+      const int c = c0 + lane * nwarps;
+      if (c < ncand) {
+        double sc = -INFINITY; int64_t id = -1;
+        if (my_row >= 0) {
+          const double den = s_qq * sqrt(my_n2);
+          sc = den > 0.0 ? my_d / den : 0.0;  // zero norm -> 0.0 (similarity.py:94-95)
+          id = my_id;
+        }
+        ex_score[c] = sc; ex_id[c] = id;
       }
-      if (lane == 0) { ex_score[c] = sc; ex_id[c] = id; }
     }
   }
   __syncthreads();
@@ -373,21 +383,24 @@ finalize_kernel(FinalizeArgs a) {
       }
     }
   };
-  // rank by counting: ids are unique, so (score desc, id asc) is a total order
-  for (int t = threadIdx.x; t < ncand; t += blockDim.x) {
-    const double s = ex_score[t]; const int64_t id = ex_id[t];
-    if (id < 0) continue;
+  // rank by counting: ids are unique, so (score desc, id asc) is a total order.  The ncand^2 comparisons are spread
+  // over the whole block (candidate t = thread / 4, every 4th opponent), partial counts meet in a quad shuffle.
+  const int nvalid = __syncthreads_count(static_cast<int>(threadIdx.x) < ncand && ex_id[threadIdx.x < ncand ? threadIdx.x : 0] >= 0);
+  for (int t0 = 0; t0 < ncand; t0 += blockDim.x / 4) {
+    const int t = t0 + (threadIdx.x >> 2), part = threadIdx.x & 3;
+    const bool live = t < ncand;
+    const double s = live ? ex_score[t] : 0.0; const int64_t id = live ? ex_id[t] : -1;
     int rank = 0;
-    for (int u = 0; u < ncand; ++u) {
-      const double su = ex_score[u]; const int64_t iu = ex_id[u];
-      if (iu >= 0 && (su > s || (su == s && iu < id))) ++rank;
-    }
-    if (rank < a.k) emit(rank, s, id);
+    if (id >= 0)
+      for (int u = part; u < ncand; u += 4) {
+        const double su = ex_score[u]; const int64_t iu = ex_id[u];
+        if (iu >= 0 && (su > s || (su == s && iu < id))) ++rank;
+      }
+    rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+    rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+    if (part == 0 && id >= 0 && rank < a.k) emit(rank, s, id);
   }
-  __shared__ int s_nvalid;
-  if (threadIdx.x == 0) { int nv = 0; for (int u = 0; u < ncand; ++u) nv += ex_id[u] >= 0; s_nvalid = nv; }
-  __syncthreads();
-  for (int t = s_nvalid + threadIdx.x; t < a.k; t += blockDim.x) emit(t, -INFINITY, -1);
+  for (int t = nvalid + threadIdx.x; t < a.k; t += blockDim.x) emit(t, -INFINITY, -1);
 }
 
 // Cross-shard merge of exact (fp64 score, id) lists: [n_shards, nq, k] -> [nq, k].

@@ -1,1 +1,3 @@
-{ echo "compute-sanitizer --tool memcheck --error-exitcode 9 python tools/memcheck_small.py   (B200, round 2: + scope masks, pre-filter, compaction, super-blocks, attention v2)"; timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/memcheck_small.py 2>&1 | grep -v "^=========$" | tail -12; } | tee gpurun_out/memcheck_r2.txt
+timeout 1200 python -m pytest tests/test_gpu_search.py -m gpu -x -q 2>&1 | tail -3
+python bench.py --no-parity --no-encoder --steps 300 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('value %.0f ms %.4f e2e %.0f kernel_ms %.4f' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['kernel_ms']), d.get('phases_ms'))"
+python tools/rows_sweep.py gpurun_out/rows_sweep_fin.json 2>&1 | tail -3
