@@ -20,6 +20,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -111,7 +114,60 @@ const AsciiClass kAscii;
 
 }  // namespace
 
+// Worker threads that live as long as the tokenizer: a batch of a few hundred chunks tokenises in well under a
+// millisecond, less than it costs to create the threads for it.  One dispatch at a time (run() returns false when
+// another caller holds the pool: that caller tokenises inline).
+struct TokPool {
+  std::vector<std::thread> threads;
+  std::mutex m, run_m;
+  std::condition_variable cv, done_cv;
+  const std::function<void()>* job = nullptr;
+  uint64_t gen = 0;
+  int pending = 0;
+  bool stop = false;
+  void start(int n) {
+    for (int i = 0; i < n; ++i)
+      threads.emplace_back([this] {
+        uint64_t seen = 0;
+        for (;;) {
+          const std::function<void()>* j;
+          {
+            std::unique_lock<std::mutex> lk(m);
+            cv.wait(lk, [&] { return stop || gen != seen; });
+            if (stop) return;
+            seen = gen; j = job;
+          }
+          (*j)();
+          {
+            std::lock_guard<std::mutex> lk(m);
+            if (--pending == 0) done_cv.notify_all();
+          }
+        }
+      });
+  }
+  bool run(const std::function<void()>& work) {          // every worker (and the caller) runs `work` once
+    std::unique_lock<std::mutex> rl(run_m, std::try_to_lock);
+    if (!rl.owns_lock() || threads.empty()) return false;
+    {
+      std::lock_guard<std::mutex> lk(m);
+      job = &work; pending = static_cast<int>(threads.size()); ++gen;
+    }
+    cv.notify_all();
+    work();
+    std::unique_lock<std::mutex> lk(m);
+    done_cv.wait(lk, [&] { return pending == 0; });
+    return true;
+  }
+  ~TokPool() {
+    { std::lock_guard<std::mutex> lk(m); stop = true; }
+    cv.notify_all();
+    for (auto& t : threads) t.join();
+  }
+};
+
 struct aur_tokenizer {
+  TokPool pool;
+  std::once_flag pool_once;
   std::unordered_map<std::string, int32_t> vocab;
   bool lower = true;
   int32_t unk = -1, cls = -1, sep = -1;
@@ -246,23 +302,26 @@ int aur_tokenize(aur_tokenizer* t, const char* texts_utf8, const int64_t* offset
     return aur::report_error(AUR_ERR_INVALID, "null argument");
   if (max_len < 2) return aur::report_error(AUR_ERR_INVALID, "max_len must be >= 2 ([CLS] and [SEP])");
   std::vector<std::vector<int32_t>> ids(static_cast<size_t>(n_texts));
-  int nt = n_threads > 0 ? n_threads : static_cast<int>(std::thread::hardware_concurrency());
-  nt = std::max(1, std::min(nt, std::max(1, n_texts / 16)));
   std::atomic<int32_t> next{0};
-  auto work = [&]() {
+  const std::function<void()> work = [&]() {
     for (;;) {
-      const int32_t b = next.fetch_add(16);
+      const int32_t b = next.fetch_add(4);
       if (b >= n_texts) break;
-      for (int32_t i = b; i < std::min(n_texts, b + 16); ++i)
+      for (int32_t i = b; i < std::min(n_texts, b + 4); ++i)
         t->encode(reinterpret_cast<const unsigned char*>(texts_utf8) + offsets[i], static_cast<size_t>(offsets[i + 1] - offsets[i]), max_len, ids[i]);
     }
   };
-  if (nt == 1) work();
-  else {
-    std::vector<std::thread> pool;
-    for (int k = 0; k < nt; ++k) pool.emplace_back(work);
-    for (auto& th : pool) th.join();
+  // n_threads == 1 (or a handful of texts): inline.  Otherwise the tokenizer's resident workers (all host cores up to 64,
+  // started on first use) share the batch; when another caller holds them this call runs inline instead of waiting.
+  bool done = false;
+  if (n_threads != 1 && n_texts > 4) {
+    std::call_once(t->pool_once, [&] {
+      const int hw = static_cast<int>(std::thread::hardware_concurrency());
+      t->pool.start(std::max(1, std::min(hw > 0 ? hw : 8, 64) - 1));
+    });
+    done = t->pool.run(work);
   }
+  if (!done) work();
   int64_t total = 0;
   cu_seqlens_out[0] = 0;
   for (int32_t i = 0; i < n_texts; ++i) {
