@@ -845,19 +845,17 @@ simtopk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       t_loop_end = TCLK();
       __syncwarp();
       if (lane == 0) atomicAdd(const_cast<int*>(epi_done), 1);   // lets the threshold warps go
-      if (use_fifo) {   // whatever is still parked meets the final threshold below
-        float tau_fin = -INFINITY;
-        if (xchg && my_tiles > 0) tau_fin = read_threshold(thr_q, epoch);
-        st.tau = fmaxf(st.tau, tau_fin);
+      // one read of the certified threshold (a global round trip) serves both the parked candidates and the final cut
+      float tau_end = -INFINITY;
+      if (xchg && my_tiles > 0) tau_end = read_threshold(thr_q, epoch);
+      st.tau = fmaxf(st.tau, tau_end);
+      if (use_fifo) {   // whatever is still parked meets the final threshold
         if (__any_sync(0xffffffffu, fcnt > 0)) st = drain_fifo(st, fifo_a, ftag_a, fcnt, list_a, ksel);
         fcnt = 0;
       }
 
       // ---- append the survivors (score >= the certified threshold, at most ksel of them)
       //      to this query's compact candidate row
-      float tau_end = -INFINITY;
-      if (xchg && my_tiles > 0) tau_end = read_threshold(thr_q, epoch);
-      st.tau = fmaxf(st.tau, tau_end);
       st = compact_list(st, list_a, ksel);
       {
         const size_t cap = static_cast<size_t>(n_tsets) * kEpiGroups * ksel;
