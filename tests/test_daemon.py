@@ -184,3 +184,51 @@ def json_meta(snap):
     import os
 
     return json.load(open(os.path.join(snap, "meta.json")))
+
+
+def test_daemon_crash_between_snapshots_loses_nothing_acknowledged(tmp_path):
+    """The deployment's durability story end to end (CPU doubles): a daemon with a snapshot directory and the mutation
+    log takes a snapshot, acknowledges more inserts and a delete, and dies without saving; the next daemon restores
+    the snapshot, replays the log and serves exactly what the first one had acknowledged."""
+    import os
+
+    emb = HashEmbedder(64)
+    snap = str(tmp_path / "snap")
+    os.makedirs(snap)
+
+    def make():          # what bootstrap.configure_from_env installs, with test doubles
+        if os.path.exists(os.path.join(snap, "meta.json")):
+            kb = R.KnowledgeBase.load(snap, emb, capacity=1024, index_loader=lambda p, cap: OracleIndex.load(p, cap))
+        else:
+            kb = R.KnowledgeBase(emb, capacity=1024, index_factory=lambda dim, cap: OracleIndex(dim, cap))
+        kb.attach_wal(os.path.join(snap, "mutations.log"))
+        return kb
+
+    R.configure(factory=make)
+    path = str(tmp_path / "kb.sock")
+    srv = serve(path, background=True, snapshot_dir=snap, save_every=10 ** 9, save_seconds=10 ** 9)
+    try:
+        kb = Client(path)
+        assert kb.insert_chunks("u", "d1", "a.md", _chunks("redis failover steps", "postgres vacuum")) == 2
+        assert kb.save()["saved"] is True
+        assert kb.insert_chunks("u", "d2", "b.md", _chunks("kafka lag alert zx77", "nginx 502 runbook")) == 2
+        assert kb.insert_chunks("u", "d1", "a.md", _chunks("redis failover steps, second edition")) == 1      # upsert
+        assert kb.delete_document_chunks("u", "d2") == 2
+        assert kb.insert_chunks("v", "d9", "z.md", _chunks("another tenant")) == 1
+        want = kb.search_knowledge_base("u", "redis failover", limit=5)
+        assert kb.health()["unsaved_mutations"] == 6
+    finally:
+        srv.shutdown(); srv.close_all(final_save=False); srv.server_close()          # "crash": no final snapshot
+    R.configure(factory=make)                                                          # a new process would start like this
+    path2 = str(tmp_path / "kb2.sock")
+    srv2 = serve(path2, background=True, snapshot_dir=snap, save_every=10 ** 9, save_seconds=10 ** 9)
+    try:
+        kb2 = Client(path2)
+        got = kb2.search_knowledge_base("u", "redis failover", limit=5)
+        assert [(r["document_id"], r["chunk_index"], r["content"]) for r in got] == [(r["document_id"], r["chunk_index"], r["content"]) for r in want]
+        assert got[0]["content"] == "redis failover steps, second edition"
+        assert kb2.get_document_chunk_count("u", "d2") == 0 and kb2.get_document_chunk_count("v", "d9") == 1
+        assert kb2.search_knowledge_base("u", "zx77", limit=3, alpha=0.0) == []       # the deleted document stays deleted
+    finally:
+        srv2.shutdown(); srv2.close_all(final_save=False); srv2.server_close()
+    R.configure(factory=lambda: (_ for _ in ()).throw(RuntimeError("backend down")))
