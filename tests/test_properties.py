@@ -73,3 +73,44 @@ def test_wordpiece_never_crashes_and_respects_limits(text):
     assert 2 <= len(ids) <= 16 and ids[0] == vocab["[CLS]"] and ids[-1] == vocab["[SEP]"]
     assert all(0 <= i < len(vocab) for i in ids)
     assert all(w and not any(c.isspace() for c in w) for w in basic_tokenize(text))
+
+
+# ---------------------------------------------------------------------- one owner, many shards (engine.MultiIndex on CPU doubles)
+ops = st.lists(st.tuples(st.sampled_from(["add", "remove", "upsert"]), st.integers(0, 10 ** 6)), min_size=1, max_size=25)
+
+
+@settings(max_examples=40, deadline=None)
+@given(ops, st.integers(1, 6), st.integers(1, 9))
+def test_multi_index_equals_one_shard_under_random_mutations(op_list, n_shards, k):
+    import numpy as np
+
+    from aurora_b200.engine import MultiIndex
+    from tests.doubles import OracleIndex
+
+    d = 16
+    one = OracleIndex(d, 4096)
+    many = MultiIndex(d, 4096, devices=list(range(n_shards)), shard_factory=lambda dd, c, dev: OracleIndex(dd, c))
+    known = []
+    for step, (op, seed) in enumerate(op_list):
+        rng = np.random.default_rng(seed)
+        if op == "add" or not known:
+            ids = np.arange(len(known) * 7 + 1000 * step, len(known) * 7 + 1000 * step + int(rng.integers(1, 8)), dtype=np.int64)
+            known += ids.tolist()
+        elif op == "upsert":
+            ids = np.array(sorted(set(rng.choice(known, size=min(len(known), 3)).tolist())), dtype=np.int64)
+        else:
+            gone = np.array(sorted(set(rng.choice(known, size=min(len(known), 3)).tolist())), dtype=np.int64)
+            assert many.remove(gone) == one.remove(gone)
+            continue
+        rows = rng.standard_normal((len(ids), d)).astype(np.float32)
+        users = rng.integers(0, 3, len(ids)).astype(np.int32)
+        orgs = rng.integers(-1, 2, len(ids)).astype(np.int32)
+        one.add(rows, ids, users, orgs); many.add(rows, ids, users, orgs)
+    Q = np.random.default_rng(1).standard_normal((3, d)).astype(np.float32)
+    for qu, qo in ((None, None), (np.array([0, 1, 2], np.int32), np.array([-1, 0, 1], np.int32))):
+        a, b = many.search(Q, k, qu, qo), one.search(Q, k, qu, qo)
+        assert np.array_equal(a[0], b[0])
+        fin = np.isfinite(b[1])
+        assert np.array_equal(np.isfinite(a[1]), fin) and np.allclose(a[1][fin], b[1][fin], atol=1e-6)
+    assert many.stats()["live"] == one.stats()["live"]
+    many.close()
