@@ -114,3 +114,29 @@ def test_multi_index_equals_one_shard_under_random_mutations(op_list, n_shards, 
         assert np.array_equal(np.isfinite(a[1]), fin) and np.allclose(a[1][fin], b[1][fin], atol=1e-6)
     assert many.stats()["live"] == one.stats()["live"]
     many.close()
+
+
+@settings(max_examples=40, deadline=None)
+@given(docs, st.lists(words, min_size=1, max_size=5).map(" ".join), st.integers(1, 8), st.booleans())
+def test_bm25_array_path_equals_loop_path(texts, query, limit, scoped):
+    """Posting lists past bm25.VECTORISE_FROM are scored as numpy arrays: same ranking and scores as the Python loop,
+    with and without a tenant pre-filter, also when only some of the query's terms take the array path."""
+    from aurora_b200 import bm25 as M
+
+    ix = BM25Index()
+    for rep in range(3):                                   # a few copies so that posting lists differ in length
+        for i, t in enumerate(texts):
+            if (i + rep) % 3 != 2:
+                ix.add(rep * 100 + i, t)
+    allowed = {d for d in ix._doc_len if d % 2 == 0} if scoped else None
+    old = M.VECTORISE_FROM
+    try:
+        M.VECTORISE_FROM = 10 ** 9
+        want = ix.search(query, limit, allowed=allowed)
+        for thr in (1, 3, 6):
+            M.VECTORISE_FROM = thr
+            got = ix.search(query, limit, allowed=allowed)
+            assert [d for d, _ in got] == [d for d, _ in want]
+            assert all(abs(a - b) < 1e-9 for (_, a), (_, b) in zip(got, want))
+    finally:
+        M.VECTORISE_FROM = old
