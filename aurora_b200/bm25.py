@@ -80,10 +80,11 @@ class BM25Index:
         return a
 
     def search(self, query: str, limit: int, allow: Optional[Callable[[int], bool]] = None,
-               allowed: Optional[set] = None) -> List[Tuple[int, float]]:
+               allowed: Optional[set] = None, allowed_sorted=None) -> List[Tuple[int, float]]:
         """Top-``limit`` (doc id, BM25 score), best first; ties by ascending id.  The pre-filter (tenant scope,
         metadata filter) comes as ``allowed`` -- a set of visible doc ids, intersected with every posting list at C
-        speed -- or as a predicate ``allow``: documents outside do not exist for this query."""
+        speed (``allowed_sorted``: the same ids as an ascending int64 array, when the caller keeps one) -- or as a
+        predicate ``allow``: documents outside do not exist for this query."""
         n_docs = len(self._doc_len)
         if n_docs == 0 or limit <= 0:
             return []
@@ -91,7 +92,7 @@ class BM25Index:
         scores: Dict[int, float] = defaultdict(float)
         doc_len = self._doc_len
         long_ids, long_contrib = [], []
-        allowed_arr = None
+        allowed_arr = allowed_sorted        # the same ids as `allowed`, ascending int64 (callers that keep one per tenant)
         for term in sorted(set(tokenize(query))):          # fixed order: equal indexes give bit-equal scores
             plist = self._postings.get(term)
             if not plist:

@@ -91,6 +91,7 @@ class KnowledgeBase:
         self._wal_path: Optional[str] = None
         self._wal_sync = True
         self._replaying = False
+        self._scope_cache: Dict[Tuple[Optional[str], Optional[str]], tuple] = {}   # tenant -> (mutations, id set, sorted ids)
 
     # ------------------------------------------------------------------ tenant codes
     def _code(self, table: Dict[str, int], key: Optional[str], create: bool) -> int:
@@ -216,6 +217,23 @@ class KnowledgeBase:
             self._log({"op": "put", "gen": gen, "user": user_id, "org": org_id, "objs": [list(o) for o in objs]})
         return len(objs)
 
+    def _tenant_scope(self, user_id: Optional[str], org_id: Optional[str]):
+        """(set, ascending int64 array) of the ids a tenant sees (its user's rows OR its org's), kept until the next
+        mutation: building them is O(tenant size), a query is not.  Caller holds the lock."""
+        key = (user_id or None, org_id or None)
+        hit = self._scope_cache.get(key)
+        if hit is not None and hit[0] == self.mutations:
+            return hit[1], hit[2]
+        by_u = self._by_user.get(user_id, set()) if user_id else set()
+        by_o = self._by_org.get(org_id, set()) if org_id else set()
+        ids = (by_u | by_o) if (by_u and by_o) else (by_u or by_o)
+        arr = np.fromiter(ids, dtype=np.int64, count=len(ids))
+        arr.sort()
+        if len(self._scope_cache) >= 256:
+            self._scope_cache.clear()
+        self._scope_cache[key] = (self.mutations, ids, arr)
+        return ids, arr
+
     def _unindex(self, rid: int, props: Dict[str, Any]) -> None:
         self._by_user.get(props.get("user_id"), set()).discard(rid)
         if props.get("org_id"):
@@ -292,14 +310,14 @@ class KnowledgeBase:
                 picked = [(rid, sc, sc) for rid, sc in dense[:limit]]
             else:
                 # keyword leg under the same pre-filter: the resolved filter's ids, else the tenant's own inverted lists
+                allowed_arr = None
                 if allowed is not None:
                     allowed_set = set(allowed)
                 elif tenant:
-                    allowed_set = (self._by_user.get(user_id, set()) if user_id else set()) | \
-                                  (self._by_org.get(org_id, set()) if org_id else set())
+                    allowed_set, allowed_arr = self._tenant_scope(user_id, org_id)
                 else:
                     allowed_set = None
-                sparse = self.sparse.search(query, _MAX_FETCH, allowed=allowed_set)
+                sparse = self.sparse.search(query, _MAX_FETCH, allowed=allowed_set, allowed_sorted=allowed_arr)
                 from .bm25 import ranked_fusion
 
                 cos = dict(dense)
